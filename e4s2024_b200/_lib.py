@@ -1,0 +1,309 @@
+"""ctypes binding of libe4s_b200.so (include/e4s_b200.h) + thin torch-tensor wrappers.
+
+There is NO fallback: if the library cannot be loaded, or a call fails, an exception is raised.
+Every wrapper enqueues on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libe4s_b200.so")
+
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_PRELU, ACT_SIGMOID, ACT_RSQRT_EPS = range(6)
+CONV_NORMAL, CONV_UP2 = 0, 1
+
+_fp = C.c_void_p
+_i32, _i64, _f32 = C.c_int32, C.c_int64, C.c_float
+
+
+class E4SConv(C.Structure):
+    """Mirror of `struct E4SConv` (include/e4s_b200.h); field order is the ABI."""
+    _fields_ = [
+        ("x", _fp), ("x_pitch", _i64),
+        ("batch", _i32), ("hin", _i32), ("win", _i32), ("cin", _i32),
+        ("in_shift", _i32), ("in_square", _i32),
+        ("w", _fp),
+        ("cout", _i32), ("cout_pad", _i32),
+        ("kh", _i32), ("kw", _i32), ("stride", _i32), ("pad", _i32), ("mode", _i32),
+        ("hout", _i32), ("wout", _i32),
+        ("in_mean", _fp), ("in_rstd", _fp),
+        ("smod", _fp), ("labels", _fp),
+        ("regions", _i32), ("lab_h", _i32), ("lab_w", _i32),
+        ("demod", _fp),
+        ("pixw", _fp), ("pixw_sb", _i64),
+        ("ch_scale", _fp), ("ch_shift", _fp),
+        ("noise", _fp), ("noise_w", _fp), ("noise_sb", _i64), ("noise_sc", _i64),
+        ("res", _fp), ("res_pitch", _i64), ("res_after_act", _i32),
+        ("act", _i32), ("act_slope", _f32), ("act_gain", _f32), ("act_prelu", _fp),
+        ("out", _fp), ("out_pitch", _i64), ("accumulate", _i32),
+    ]
+
+
+EXPORTS = [
+    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_tc",
+    "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
+    "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
+    "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
+    "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
+    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32",
+]
+
+_lib = None
+
+
+class E4SError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise E4SError(f"{LIB_PATH} is missing: run `python -m e4s2024_b200.build` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.e4s_last_error.restype = C.c_char_p
+        _lib.e4s_launch_count.restype = C.c_int64
+        _lib.e4s_chan_stats_ws_bytes.restype = C.c_int64
+        _lib.e4s_pack_weights_tc_bytes.restype = C.c_int64
+        if _lib.e4s_sizeof_conv() != C.sizeof(E4SConv):
+            raise E4SError(f"struct E4SConv mismatch: C {_lib.e4s_sizeof_conv()} vs ctypes {C.sizeof(E4SConv)}")
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise E4SError(f"{what} failed ({rc}): {lib().e4s_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().e4s_launch_count())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=torch.float32, contig: bool = True):
+    if not t.is_cuda:
+        raise E4SError("e4s2024_b200 kernels need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise E4SError(f"expected {dtype}, got {t.dtype}")
+    if contig and not t.is_contiguous():
+        raise E4SError("tensor must be contiguous")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# wrappers (one per C entry point)
+# ------------------------------------------------------------------------------------------------
+
+def conv(params: E4SConv, tc_weights: Optional[torch.Tensor] = None):
+    if tc_weights is not None:
+        _check(lib().e4s_conv_tc(C.byref(params), C.c_void_p(tc_weights.data_ptr()), _stream()), "e4s_conv_tc")
+    else:
+        _check(lib().e4s_conv_f32(C.byref(params), _stream()), "e4s_conv_f32")
+
+
+def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cout: int, cout_pad: int) -> torch.Tensor:
+    nbytes = int(lib().e4s_pack_weights_tc_bytes(phases, k, cout))
+    if nbytes <= 0:
+        raise E4SError("e4s_pack_weights_tc_bytes: unsupported shape")
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w_f32.device)
+    _check(lib().e4s_pack_weights_tc(C.c_void_p(w_f32.data_ptr()), phases, k, cout, cout_pad, C.c_void_p(out.data_ptr()),
+                                     _stream()), "e4s_pack_weights_tc")
+    return out
+
+
+def upfirdn2d(x: torch.Tensor, kernel: torch.Tensor, up: int, down: int, pad0: int, pad1: int) -> torch.Tensor:
+    _req(x), _req(kernel)
+    b, c, h, w = x.shape
+    kh, kw = kernel.shape
+    oh = (h * up + pad0 + pad1 - kh + down) // down
+    ow = (w * up + pad0 + pad1 - kw + down) // down
+    out = torch.empty(b, c, max(oh, 0), max(ow, 0), device=x.device, dtype=x.dtype)
+    _check(lib().e4s_upfirdn2d_f32(_fp(x.data_ptr()), _fp(kernel.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w,
+                                   kh, kw, up, up, down, down, pad0, pad1, pad0, pad1, _stream()), "e4s_upfirdn2d_f32")
+    return out
+
+
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], slope: float, scale: float) -> torch.Tensor:
+    _req(x)
+    y = torch.empty_like(x)
+    channels = x.shape[1] if x.ndim > 1 else 1
+    inner = 1
+    for d in x.shape[2:]:
+        inner *= d
+    _check(lib().e4s_bias_act_f32(_fp(x.data_ptr()), _fp(_p(bias)), _fp(y.data_ptr()), C.c_int64(x.numel()), C.c_int64(inner),
+                                  channels, _f32(slope), _f32(scale), _stream()), "e4s_bias_act_f32")
+    return y
+
+
+def noise_bias_act_nhwc(x, noise, noise_w, noise_sb, noise_sc, bias, slope, scale):
+    b, h, w, c = x.shape
+    _check(lib().e4s_noise_bias_act_nhwc_f32(_fp(x.data_ptr()), b, h, w, c, _fp(_p(noise)), _fp(_p(noise_w)), C.c_int64(noise_sb),
+                                             C.c_int64(noise_sc), _fp(_p(bias)), _f32(slope), _f32(scale), _stream()),
+           "e4s_noise_bias_act_nhwc_f32")
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    _req(x)
+    b, c, h, w = x.shape
+    c_pad = c if c_pad is None else c_pad
+    y = torch.empty(b, h, w, c_pad, device=x.device, dtype=x.dtype)
+    _check(lib().e4s_nchw_to_nhwc_f32(_fp(x.data_ptr()), _fp(y.data_ptr()), b, c, h, w, c_pad, _stream()), "e4s_nchw_to_nhwc_f32")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    """x: [B,H,W,P] contiguous; the first c channels are converted."""
+    _req(x)
+    b, h, w, pitch = x.shape
+    c = pitch if c is None else c
+    y = torch.empty(b, c, h, w, device=x.device, dtype=x.dtype)
+    _check(lib().e4s_nhwc_to_nchw_f32(_fp(x.data_ptr()), C.c_int64(pitch), _fp(y.data_ptr()), b, c, h, w, _stream()),
+           "e4s_nhwc_to_nchw_f32")
+    return y
+
+
+def mask_labels(mask: torch.Tensor):
+    """-> (labels u8 [B,H,W], flags int32[1]); flags[0] > 0 means the mask is not one-hot/empty per pixel."""
+    _req(mask)
+    b, k, h, w = mask.shape
+    labels = torch.empty(b, h, w, device=mask.device, dtype=torch.uint8)
+    flags = torch.zeros(1, device=mask.device, dtype=torch.int32)
+    _check(lib().e4s_mask_labels(_fp(mask.data_ptr()), b, k, h, w, _fp(labels.data_ptr()), _fp(flags.data_ptr()), _stream()),
+           "e4s_mask_labels")
+    return labels, flags
+
+
+def labels_to_onehot(labels: torch.Tensor, k: int) -> torch.Tensor:
+    _req(labels, torch.uint8)
+    b, h, w = labels.shape
+    out = torch.empty(b, k, h, w, device=labels.device, dtype=torch.float32)
+    _check(lib().e4s_labels_to_onehot_f32(_fp(labels.data_ptr()), b, k, h, w, _fp(out.data_ptr()), _stream()), "e4s_labels_to_onehot_f32")
+    return out
+
+
+def torgb(x_nhwc, cin, smod, wrgb, labels, regions, lab_hw, pixw, pixw_sb, bias, skip, fir, rgb, accumulate):
+    b, h, w, pitch = x_nhwc.shape
+    lh, lw = lab_hw
+    _check(lib().e4s_torgb_f32(_fp(x_nhwc.data_ptr()), C.c_int64(pitch), b, h, w, cin, _fp(smod.data_ptr()), _fp(wrgb.data_ptr()),
+                               _fp(_p(labels)), regions, lh, lw, _fp(pixw), C.c_int64(pixw_sb), _fp(_p(bias)), _fp(_p(skip)),
+                               _fp(_p(fir)), _fp(rgb.data_ptr()), int(accumulate), _stream()), "e4s_torgb_f32")
+
+
+_ws_cache = {}
+
+
+def _stats_ws(device, batch, c) -> torch.Tensor:
+    n = int(lib().e4s_chan_stats_ws_bytes(batch, c))
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def chan_stats(x_nhwc: torch.Tensor, c: int, eps: float = 1e-5, want_rstd: bool = True):
+    """x [B,H,W,P]: (mean [B,c], rstd [B,c] or None) over H*W of the first c channels."""
+    b, h, w, pitch = x_nhwc.shape
+    mean = torch.empty(b, c, device=x_nhwc.device, dtype=torch.float32)
+    rstd = torch.empty(b, c, device=x_nhwc.device, dtype=torch.float32) if want_rstd else None
+    ws = _stats_ws(x_nhwc.device, b, c)
+    _check(lib().e4s_chan_stats_f32(_fp(x_nhwc.data_ptr()), C.c_int64(pitch), b, h * w, c, _f32(eps), _fp(mean.data_ptr()),
+                                    _fp(_p(rstd)), _fp(ws.data_ptr()), _stream()), "e4s_chan_stats_f32")
+    return mean, rstd
+
+
+def vec_fc(x: torch.Tensor, w: torch.Tensor, scale, shift, act: int) -> torch.Tensor:
+    """x [B,cin] (row stride x.stride(0)), w [cout,cin] -> [B,cout]."""
+    b, cin = x.shape
+    cout = w.shape[0]
+    y = torch.empty(b, cout, device=x.device, dtype=torch.float32)
+    _check(lib().e4s_vec_fc_f32(_fp(x.data_ptr()), C.c_int64(x.stride(0)), _fp(w.data_ptr()), _fp(_p(scale)), _fp(_p(shift)),
+                                _fp(y.data_ptr()), b, cin, cout, act, _stream()), "e4s_vec_fc_f32")
+    return y
+
+
+def residual_combine(a, c, a_stats=None, gate=None, gate_plus_one=False, r=None, r_sub=1, r_stats=None, relu=False,
+                     prelu=None, out=None):
+    """a [B,H,W,Pa]; r [B,Hr,Wr,Pr] or None -> out [B,H,W,c] (see e4s_residual_combine_f32)."""
+    b, h, w, pa = a.shape
+    if out is None:
+        out = torch.empty(b, h, w, c, device=a.device, dtype=torch.float32)
+    am, ar = a_stats if a_stats is not None else (None, None)
+    rm, rr = r_stats if r_stats is not None else (None, None)
+    rh, rw, pr = (r.shape[1], r.shape[2], r.shape[3]) if r is not None else (0, 0, 0)
+    _check(lib().e4s_residual_combine_f32(_fp(a.data_ptr()), C.c_int64(pa), _fp(_p(am)), _fp(_p(ar)), _fp(_p(gate)),
+                                          int(gate_plus_one), _fp(_p(r)), C.c_int64(pr), rh, rw, r_sub, _fp(_p(rm)), _fp(_p(rr)),
+                                          int(relu), _fp(_p(prelu)), _fp(out.data_ptr()), C.c_int64(out.shape[3]), b, h, w, c, _stream()),
+           "e4s_residual_combine_f32")
+    return out
+
+
+def masked_mean(feat_nhwc, c, mask, codes, c_off):
+    """codes [B,K,D] gets codes[:, :, c_off:c_off+c] = per-region mean of feat."""
+    b, h, w, pitch = feat_nhwc.shape
+    _, k, mh, mw = mask.shape
+    _check(lib().e4s_masked_mean_f32(_fp(feat_nhwc.data_ptr()), C.c_int64(pitch), b, h, w, c, _fp(mask.data_ptr()), k, mh, mw,
+                                     _fp(codes.data_ptr()), C.c_int64(codes.stride(0)), C.c_int64(codes.stride(1)), c_off,
+                                     _stream()), "e4s_masked_mean_f32")
+
+
+def resize_bilinear_nchw_to_nhwc(x, hout, wout, c_pad, align_corners=False):
+    _req(x)
+    b, c, h, w = x.shape
+    y = torch.empty(b, hout, wout, c_pad, device=x.device, dtype=torch.float32)
+    _check(lib().e4s_resize_bilinear_nchw_to_nhwc_f32(_fp(x.data_ptr()), b, c, h, w, _fp(y.data_ptr()), hout, wout, c_pad,
+                                                      int(align_corners), _stream()), "e4s_resize_bilinear_nchw_to_nhwc_f32")
+    return y
+
+
+def resize_bilinear_nhwc_to_nchw(x_nhwc, c, hout, wout, align_corners=True):
+    b, h, w, pitch = x_nhwc.shape
+    y = torch.empty(b, c, hout, wout, device=x_nhwc.device, dtype=torch.float32)
+    _check(lib().e4s_resize_bilinear_nhwc_to_nchw_f32(_fp(x_nhwc.data_ptr()), C.c_int64(pitch), b, c, h, w, _fp(y.data_ptr()), hout,
+                                                      wout, int(align_corners), _stream()), "e4s_resize_bilinear_nhwc_to_nchw_f32")
+    return y
+
+
+def maxpool3x3s2(x_nhwc):
+    b, h, w, c = x_nhwc.shape
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    y = torch.empty(b, ho, wo, c, device=x_nhwc.device, dtype=torch.float32)
+    _check(lib().e4s_maxpool3x3s2_nhwc_f32(_fp(x_nhwc.data_ptr()), b, h, w, c, _fp(y.data_ptr()), _stream()), "e4s_maxpool3x3s2_nhwc_f32")
+    return y
+
+
+def upsample_argmax(logits_nhwc, c, hout, wout, lut=None):
+    b, h, w, pitch = logits_nhwc.shape
+    labels = torch.empty(b, hout, wout, device=logits_nhwc.device, dtype=torch.uint8)
+    _check(lib().e4s_upsample_argmax_u8(_fp(logits_nhwc.data_ptr()), C.c_int64(pitch), b, c, h, w, hout, wout, _fp(_p(lut)),
+                                        _fp(labels.data_ptr()), _stream()), "e4s_upsample_argmax_u8")
+    return labels
+
+
+def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
+    _req(x)
+    b, c, h, w = x.shape
+    if c != 3:
+        raise E4SError("bicubic_down_norm expects 3 channels")
+    tmp = torch.empty(b, 3, h // factor, w, device=x.device, dtype=torch.float32)
+    y = torch.empty(b, h // factor, w // factor, c_pad, device=x.device, dtype=torch.float32)
+    _check(lib().e4s_bicubic_down_norm_f32(_fp(x.data_ptr()), b, h, w, factor, _fp(taps.data_ptr()), _fp(mean.data_ptr()),
+                                           _fp(std.data_ptr()), _fp(tmp.data_ptr()), _fp(y.data_ptr()), c_pad, int(clamp),
+                                           _stream()),
+           "e4s_bicubic_down_norm_f32")
+    return y

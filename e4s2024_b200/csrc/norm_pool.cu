@@ -1,0 +1,298 @@
+// Reductions and gating of the encoder / BiSeNet: per-(sample,channel) statistics (InstanceNorm,
+// global average pooling), tiny per-sample FC layers (SE, attention), the fused
+// normalise * gate + shortcut tail, masked region means and 3x3/2 max pooling.  All NHWC fp32,
+// all deterministic (fixed reduction trees, fp64 partial sums) so results do not depend on batch size.
+#include "common.cuh"
+
+namespace e4s {
+
+constexpr int STATS_MAX_SPLIT = 32;
+
+__host__ __device__ inline int stats_split(int batch, int hw, int c) {
+  int groups = batch * ((c + 31) / 32);
+  int s = (592 + groups - 1) / groups;
+  int cap = hw / 64;
+  if (s > cap) s = cap;
+  if (s > STATS_MAX_SPLIT) s = STATS_MAX_SPLIT;
+  return s < 1 ? 1 : s;
+}
+
+// partial[b][s][c] = (sum, sumsq) over the s-th slice of pixels
+__global__ void __launch_bounds__(256) chan_stats_partial_kernel(const float* __restrict__ x, int64_t pitch, int hw, int c,
+                                                                 int split, double2* __restrict__ partial) {
+  __shared__ double2 red[8][32];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, s = blockIdx.y, b = blockIdx.z;
+  const int per = (hw + split - 1) / split;
+  const int p0 = s * per, p1 = min(hw, p0 + per);
+  const int ch = c0 + cx;
+  double sum = 0.0, sq = 0.0;
+  if (ch < c) {
+    const float* xp = x + (int64_t)b * hw * pitch + ch;
+    for (int p = p0 + py; p < p1; p += 8) {
+      float v = __ldg(xp + (int64_t)p * pitch);
+      sum += (double)v;
+      sq += (double)v * (double)v;
+    }
+  }
+  red[py][cx] = make_double2(sum, sq);
+  __syncthreads();
+  if (py == 0 && ch < c) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      sum += red[i][cx].x;
+      sq += red[i][cx].y;
+    }
+    partial[((int64_t)b * split + s) * c + ch] = make_double2(sum, sq);
+  }
+}
+
+__global__ void chan_stats_final_kernel(const double2* __restrict__ partial, int batch, int hw, int c, int split, float eps,
+                                        float* __restrict__ mean, float* __restrict__ rstd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * c) return;
+  int b = i / c, ch = i - b * c;
+  double sum = 0.0, sq = 0.0;
+  for (int s = 0; s < split; ++s) {
+    double2 v = partial[((int64_t)b * split + s) * c + ch];
+    sum += v.x;
+    sq += v.y;
+  }
+  double m = sum / hw;
+  double var = sq / hw - m * m;
+  if (var < 0.0) var = 0.0;
+  if (mean) mean[i] = (float)m;
+  if (rstd) rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// one warp per output feature
+__global__ void __launch_bounds__(256) vec_fc_kernel(const float* __restrict__ x, int64_t x_stride,
+                                                     const float* __restrict__ w, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, float* __restrict__ y, int cin,
+                                                     int cout, int act) {
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= cout) return;
+  const float* xr = x + (int64_t)b * x_stride;
+  const float* wr = w + (int64_t)o * cin;
+  float acc = 0.f;
+  for (int i = lane; i < cin; i += 32) acc = fmaf(__ldg(wr + i), __ldg(xr + i), acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    if (scale) acc *= __ldg(scale + o);
+    if (shift) acc += __ldg(shift + o);
+    if (act == E4S_ACT_RELU) acc = fmaxf(acc, 0.f);
+    else if (act == E4S_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+    y[(int64_t)b * cout + o] = acc;
+  }
+}
+
+__global__ void residual_combine_kernel(const float* __restrict__ a, int64_t a_pitch, const float* __restrict__ a_mean,
+                                        const float* __restrict__ a_rstd, const float* __restrict__ gate, int gate_plus_one,
+                                        const float* __restrict__ r, int64_t r_pitch, int r_h, int r_w, int r_sub,
+                                        const float* __restrict__ r_mean, const float* __restrict__ r_rstd, int relu,
+                                        const float* __restrict__ prelu, float* __restrict__ out, int64_t out_pitch, int h, int w, int c, int64_t total4) {
+  const int c4 = c >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % c4);
+    const int64_t pix = i / c4;
+    const int ch = cq * 4;
+    const int hw = h * w;
+    const int b = (int)(pix / hw);
+    const int rem = (int)(pix - (int64_t)b * hw);
+    float4 v = __ldg(reinterpret_cast<const float4*>(a + pix * a_pitch + ch));
+    if (a_mean) {
+      float4 m = __ldg(reinterpret_cast<const float4*>(a_mean + (int64_t)b * c + ch));
+      float4 s = __ldg(reinterpret_cast<const float4*>(a_rstd + (int64_t)b * c + ch));
+      v.x = (v.x - m.x) * s.x; v.y = (v.y - m.y) * s.y; v.z = (v.z - m.z) * s.z; v.w = (v.w - m.w) * s.w;
+    }
+    if (gate) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gate + (int64_t)b * c + ch));
+      if (gate_plus_one) {  // feat*g + feat, evaluated like the reference (mul then add)
+        v.x = v.x * g.x + v.x; v.y = v.y * g.y + v.y; v.z = v.z * g.z + v.z; v.w = v.w * g.w + v.w;
+      } else {
+        v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+      }
+    }
+    if (r) {
+      const int y = rem / w, xx = rem - y * w;
+      int ry, rx;
+      if (r_sub > 1) {
+        ry = y * r_sub;
+        rx = xx * r_sub;
+      } else {
+        ry = nearest_src(y, r_h, h);
+        rx = nearest_src(xx, r_w, w);
+      }
+      float4 q = __ldg(reinterpret_cast<const float4*>(r + (((int64_t)b * r_h + ry) * r_w + rx) * r_pitch + ch));
+      if (r_mean) {
+        float4 m = __ldg(reinterpret_cast<const float4*>(r_mean + (int64_t)b * c + ch));
+        float4 s = __ldg(reinterpret_cast<const float4*>(r_rstd + (int64_t)b * c + ch));
+        q.x = (q.x - m.x) * s.x; q.y = (q.y - m.y) * s.y; q.z = (q.z - m.z) * s.z; q.w = (q.w - m.w) * s.w;
+      }
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (prelu) {
+      float4 sl = __ldg(reinterpret_cast<const float4*>(prelu + ch));
+      v.x = v.x < 0.f ? v.x * sl.x : v.x; v.y = v.y < 0.f ? v.y * sl.y : v.y;
+      v.z = v.z < 0.f ? v.z * sl.z : v.z; v.w = v.w < 0.f ? v.w * sl.w : v.w;
+    }
+    *reinterpret_cast<float4*>(out + pix * out_pitch + ch) = v;
+  }
+}
+
+constexpr int MM_MAXK = 16;
+
+__global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restrict__ feat, int64_t f_pitch, int h, int w,
+                                                          int c, const float* __restrict__ mask, int k, int mh, int mw,
+                                                          float* __restrict__ codes, int64_t sb, int64_t sk, int c_off) {
+  __shared__ double red[8][32];
+  __shared__ int redc[8];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, b = blockIdx.y;
+  const int ch = c0 + cx;
+  const int hw = h * w;
+  double acc[MM_MAXK];
+  int cnt[MM_MAXK];
+#pragma unroll
+  for (int j = 0; j < MM_MAXK; ++j) {
+    acc[j] = 0.0;
+    cnt[j] = 0;
+  }
+  const float* mb = mask + (int64_t)b * k * mh * mw;
+  for (int p = py; p < hw; p += 8) {
+    const int y = p / w, xx = p - y * w;
+    const int sy = nearest_src(y, mh, h), sx = nearest_src(xx, mw, w);
+    const float v = ch < c ? __ldg(feat + ((int64_t)b * hw + p) * f_pitch + ch) : 0.f;
+#pragma unroll
+    for (int j = 0; j < MM_MAXK; ++j) {
+      if (j < k && __ldg(mb + ((int64_t)j * mh + sy) * mw + sx) != 0.f) {
+        acc[j] += (double)v;
+        cnt[j] += 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MM_MAXK; ++j) {
+    if (j >= k) break;
+    __syncthreads();
+    red[py][cx] = acc[j];
+    if (cx == 0) redc[py] = cnt[j];
+    __syncthreads();
+    if (py == 0 && ch < c) {
+      double s = 0.0;
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s += red[i][cx];
+        n += redc[i];
+      }
+      codes[(int64_t)b * sb + (int64_t)j * sk + c_off + ch] = n > 0 ? (float)(s / n) : 0.f;
+    }
+  }
+}
+
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int h, int w, int c, int ho, int wo, float* __restrict__ y,
+                                    int64_t total4) {
+  const int c4 = c >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % c4);
+    int64_t t = i / c4;
+    const int ox = (int)(t % wo);
+    t /= wo;
+    const int oy = (int)(t % ho);
+    const int b = (int)(t / ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)b * h + iy) * w + ix) * c + cq * 4));
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = m;
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int block) {
+  int64_t g = ceil_div64(n, block);
+  const int64_t cap = 148 * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace e4s
+
+using namespace e4s;
+
+extern "C" int64_t e4s_chan_stats_ws_bytes(int batch, int c) {
+  return (int64_t)batch * STATS_MAX_SPLIT * c * (int64_t)sizeof(double2);
+}
+
+extern "C" int e4s_chan_stats_f32(const float* x, int64_t x_pitch, int batch, int hw, int c, float eps, float* mean,
+                                  float* rstd, void* ws, void* stream) {
+  E4S_REQUIRE(x && ws && (mean || rstd), "chan_stats: null pointer");
+  E4S_REQUIRE(batch > 0 && hw > 0 && c > 0 && x_pitch >= c, "chan_stats: bad shape");
+  E4S_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "chan_stats: workspace must be 16-byte aligned");
+  const int split = stats_split(batch, hw, c);
+  dim3 grid(ceil_div(c, 32), split, batch);
+  chan_stats_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_pitch, hw, c, split, reinterpret_cast<double2*>(ws));
+  int rc = check_launch("chan_stats_partial");
+  if (rc) return rc;
+  chan_stats_final_kernel<<<ceil_div(batch * c, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const double2*>(ws), batch,
+                                                                                   hw, c, split, eps, mean, rstd);
+  return check_launch("chan_stats_final");
+}
+
+extern "C" int e4s_vec_fc_f32(const float* x, int64_t x_stride, const float* w, const float* scale, const float* shift,
+                              float* y, int batch, int cin, int cout, int act, void* stream) {
+  E4S_REQUIRE(x && w && y && batch > 0 && cin > 0 && cout > 0, "vec_fc: bad args");
+  E4S_REQUIRE(act == E4S_ACT_NONE || act == E4S_ACT_RELU || act == E4S_ACT_SIGMOID, "vec_fc: unsupported act %d", act);
+  dim3 grid(ceil_div(cout, 8), batch);
+  vec_fc_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_stride, w, scale, shift, y, cin, cout, act);
+  return check_launch("vec_fc");
+}
+
+extern "C" int e4s_residual_combine_f32(const float* a, int64_t a_pitch, const float* a_mean, const float* a_rstd,
+                                        const float* gate, int gate_plus_one, const float* r, int64_t r_pitch, int r_h,
+                                        int r_w, int r_sub, const float* r_mean, const float* r_rstd, int relu, const float* prelu,
+                                        float* out, int64_t out_pitch, int batch, int h, int w, int c, void* stream) {
+  E4S_REQUIRE(a && out && batch > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "residual_combine: bad args");
+  E4S_REQUIRE(a_pitch % 4 == 0 && out_pitch % 4 == 0 && (!r || r_pitch % 4 == 0), "residual_combine: pitches must be multiples of 4");
+  E4S_REQUIRE(!a_mean || a_rstd, "residual_combine: a_mean without a_rstd");
+  E4S_REQUIRE(!r || (r_h > 0 && r_w > 0 && r_sub >= 1), "residual_combine: bad residual geometry");
+  E4S_REQUIRE(!r || r_sub == 1 || ((h - 1) * r_sub < r_h && (w - 1) * r_sub < r_w), "residual_combine: subsampled residual out of range");
+  int64_t total4 = (int64_t)batch * h * w * (c / 4);
+  residual_combine_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(a, a_pitch, a_mean, a_rstd, gate, gate_plus_one, r,
+                                                                                r_pitch, r_h, r_w, r_sub, r_mean, r_rstd, relu,
+                                                                                prelu, out, out_pitch, h, w, c, total4);
+  return check_launch("residual_combine");
+}
+
+extern "C" int e4s_masked_mean_f32(const float* feat, int64_t f_pitch, int batch, int h, int w, int c, const float* mask, int k,
+                                   int mh, int mw, float* codes, int64_t codes_stride_b, int64_t codes_stride_k, int c_off,
+                                   void* stream) {
+  E4S_REQUIRE(feat && mask && codes && batch > 0 && h > 0 && w > 0 && c > 0, "masked_mean: bad args");
+  E4S_REQUIRE(k > 0 && k <= MM_MAXK && mh > 0 && mw > 0, "masked_mean: k must be in 1..%d", MM_MAXK);
+  dim3 grid(ceil_div(c, 32), batch);
+  masked_mean_kernel<<<grid, 256, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, mask, k, mh, mw, codes, codes_stride_b,
+                                                         codes_stride_k, c_off);
+  return check_launch("masked_mean");
+}
+
+extern "C" int e4s_maxpool3x3s2_nhwc_f32(const float* x, int batch, int h, int w, int c, float* y, void* stream) {
+  E4S_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool: bad args");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  int64_t total4 = (int64_t)batch * ho * wo * (c / 4);
+  maxpool3x3s2_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(x, h, w, c, ho, wo, y, total4);
+  return check_launch("maxpool3x3s2");
+}

@@ -1,0 +1,406 @@
+// Bandwidth-bound kernels of the hot path: layout adapters, upfirdn2d, bias+leaky-ReLU, mask -> label
+// maps, ToRGB (+bias +FIR-upsampled skip), one-hot.  All are coalesced / smem-staged streaming kernels;
+// grids are sized from the problem (many waves on 148 SMs).
+#include "common.cuh"
+
+namespace e4s {
+
+// ------------------------------------------------------------------------------------------------
+// layout adapters (module API is NCHW, the engine is NHWC)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int c, int hw, int c_pad) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    int cc = c0 + i, pp = p0 + tx;
+    tile[i][tx] = (cc < c && pp < hw) ? x[((int64_t)b * c + cc) * hw + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int pp = p0 + i, cc = c0 + tx;
+    if (pp < hw && cc < c_pad) y[((int64_t)b * hw + pp) * c_pad + cc] = tile[tx][i];
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int64_t pitch, float* __restrict__ y, int c, int hw) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    int pp = p0 + i, cc = c0 + tx;
+    tile[i][tx] = (pp < hw && cc < c) ? x[((int64_t)b * hw + pp) * pitch + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int cc = c0 + i, pp = p0 + tx;
+    if (cc < c && pp < hw) y[((int64_t)b * c + cc) * hw + pp] = tile[tx][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// upfirdn2d
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// Tiled variant for down == 1, up in {1,2}, taps <= 4x4 (the two modes the generator uses):
+// a 16x64 output tile per CTA, input tile + flipped taps staged in shared memory.
+template <int UP>
+__global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ k,
+                                                             float* __restrict__ out, int in_h, int in_w, int out_h,
+                                                             int out_w, int kh, int kw, int pad_x0, int pad_y0) {
+  constexpr int TH = 16, TW = 64;
+  constexpr int IH = (TH + 3) / UP + 2, IW = (TW + 3) / UP + 2;
+  __shared__ float sk[4][4];
+  __shared__ float sx[IH][IW + 1];
+  const int plane = blockIdx.z;
+  const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    int ky = tid >> 2, kx = tid & 3;
+    sk[ky][kx] = (ky < kh && kx < kw) ? k[(kh - 1 - ky) * kw + (kw - 1 - kx)] : 0.f;  // flipped taps
+  }
+  const int iy0 = floor_div(oy0 - pad_y0, UP), ix0 = floor_div(ox0 - pad_x0, UP);
+  const float* xp = x + (int64_t)plane * in_h * in_w;
+  for (int i = tid; i < IH * IW; i += 256) {
+    int ly = i / IW, lx = i - ly * IW;
+    int iy = iy0 + ly, ix = ix0 + lx;
+    sx[ly][lx] = (iy >= 0 && iy < in_h && ix >= 0 && ix < in_w) ? __ldg(xp + (int64_t)iy * in_w + ix) : 0.f;
+  }
+  __syncthreads();
+  const int tx = tid & 63, tyb = tid >> 6;
+  const int ox = ox0 + tx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int oy = oy0 + tyb + 4 * j;
+    if (oy >= out_h || ox >= out_w) continue;
+    const int my = oy - pad_y0, mx = ox - pad_x0;  // window origin in the zero-inserted image
+    float v = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int uy = my + ky;
+      if (UP == 2 && (uy & 1)) continue;
+      const int ly = (UP == 2 ? (uy >> 1) : uy) - iy0;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ux = mx + kx;
+        if (UP == 2 && (ux & 1)) continue;
+        const int lx = (UP == 2 ? (ux >> 1) : ux) - ix0;
+        v = fmaf(sx[ly][lx], sk[ky][kx], v);
+      }
+    }
+    out[((int64_t)plane * out_h + oy) * out_w + ox] = v;
+  }
+}
+
+// Generic variant (any up/down/pad, any tap count): one thread per output, taps through L1.
+__global__ void upfirdn2d_generic_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ out,
+                                         int64_t total, int in_h, int in_w, int out_h, int out_w, int kh, int kw, int up_x,
+                                         int up_y, int down_x, int down_y, int pad_x0, int pad_y0) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ox = (int)(i % out_w);
+    int64_t t = i / out_w;
+    int oy = (int)(t % out_h);
+    int64_t plane = t / out_h;
+    const float* xp = x + plane * in_h * in_w;
+    const int my = oy * down_y - pad_y0, mx = ox * down_x - pad_x0;
+    float v = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      int uy = my + ky;
+      if (uy < 0 || uy % up_y) continue;
+      int iy = uy / up_y;
+      if (iy >= in_h) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        int ux = mx + kx;
+        if (ux < 0 || ux % up_x) continue;
+        int ix = ux / up_x;
+        if (ix >= in_w) continue;
+        v = fmaf(__ldg(xp + (int64_t)iy * in_w + ix), __ldg(k + (kh - 1 - ky) * kw + (kw - 1 - kx)), v);
+      }
+    }
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias + leaky ReLU (fused_bias_act case 30)
+// ------------------------------------------------------------------------------------------------
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+                                int64_t n, int64_t inner, int channels, float slope, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (bias) v += __ldg(bias + (i / inner) % channels);
+    y[i] = (v < 0.f ? v * slope : v) * scale;
+  }
+}
+
+__global__ void bias_act_vec4_kernel(const float4* __restrict__ x, const float* __restrict__ bias, float4* __restrict__ y,
+                                     int64_t n4, int64_t inner4, int channels, float slope, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    float b = bias ? __ldg(bias + (i / inner4) % channels) : 0.f;  // inner % 4 == 0: one channel per float4
+    v.x += b; v.y += b; v.z += b; v.w += b;
+    v.x = (v.x < 0.f ? v.x * slope : v.x) * scale;
+    v.y = (v.y < 0.f ? v.y * slope : v.y) * scale;
+    v.z = (v.z < 0.f ? v.z * slope : v.z) * scale;
+    v.w = (v.w < 0.f ? v.w * slope : v.w) * scale;
+    y[i] = v;
+  }
+}
+
+__global__ void noise_bias_act_nhwc_kernel(float* __restrict__ x, int64_t total, int hw, int w_, int c,
+                                           const float* __restrict__ noise, const float* __restrict__ noise_w,
+                                           int64_t nsb, int64_t nsc, const float* __restrict__ bias, float slope,
+                                           float scale) {
+  const float nw = noise ? __ldg(noise_w) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c);
+    int64_t pix = i / c;
+    int b = (int)(pix / hw);
+    int p = (int)(pix - (int64_t)b * hw);
+    float v = x[i];
+    if (noise) v += nw * __ldg(noise + b * nsb + ch * nsc + p);
+    if (bias) v += __ldg(bias + ch);
+    x[i] = (v < 0.f ? v * slope : v) * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask -> label map, one-hot
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_labels_kernel(const float* __restrict__ mask, int k, int64_t hw, int64_t total,
+                                   uint8_t* __restrict__ labels, int32_t* __restrict__ flags) {
+  int bad = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = i / hw, p = i - b * hw;
+    const float* m = mask + b * k * hw + p;
+    int ones = 0, nonzero = 0, idx = k;
+    float best = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float v = __ldg(m + (int64_t)j * hw);
+      if (v != 0.f) {
+        ++nonzero;
+        if (v == 1.f) ++ones;
+        if (idx == k || v > best) { idx = j; best = v; }
+      }
+    }
+    if (!(nonzero == 1 && ones == 1)) bad = 1;
+    labels[i] = (uint8_t)(idx < k ? idx : 0);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicAdd(flags, 1);
+}
+
+__global__ void labels_to_onehot_kernel(const uint8_t* __restrict__ labels, int k, int64_t hw, int64_t total,
+                                        float* __restrict__ onehot) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i % hw;
+    int64_t t = i / hw;
+    int j = (int)(t % k);
+    int64_t b = t / k;
+    onehot[i] = (labels[b * hw + p] == j) ? 1.f : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip, NHWC in -> NCHW out
+// LP lanes cooperate on one pixel (float4 channel slices), warp-shuffle reduction.
+// ------------------------------------------------------------------------------------------------
+template <int LP>
+__global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, int64_t x_pitch, int64_t npix, int h, int w,
+                                                    int cin, const float* __restrict__ smod, const float* __restrict__ wrgb,
+                                                    const uint8_t* __restrict__ labels, int regions, int lab_h, int lab_w,
+                                                    const float* __restrict__ pixw, int64_t pixw_sb,
+                                                    const float* __restrict__ bias, const float* __restrict__ skip,
+                                                    const float* __restrict__ fir, float* __restrict__ rgb, int accumulate) {
+  constexpr int PPW = 32 / LP;  // pixels per warp step
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LP, ll = lane % LP;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int hw = h * w;
+  for (int64_t base = warp * PPW; base < npix; base += nwarps * PPW) {
+    const int64_t pix = base + sub;
+    const bool ok = pix < npix;
+    int b = 0, y = 0, xx = 0, r = 0, sy = 0, sx = 0;
+    if (ok) {
+      b = (int)(pix / hw);
+      int rem = (int)(pix - (int64_t)b * hw);
+      y = rem / w;
+      xx = rem - y * w;
+      if (labels || pixw) {
+        sy = nearest_src(y, lab_h, h);
+        sx = nearest_src(xx, lab_w, w);
+      }
+      if (labels) r = labels[((int64_t)b * lab_h + sy) * lab_w + sx];
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (ok) {
+      const float* xr = x + pix * x_pitch;
+      const float* sr = smod + ((int64_t)b * regions + r) * cin;
+      for (int ci = ll * 4; ci < cin; ci += LP * 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(xr + ci));
+        const float4 sm = __ldg(reinterpret_cast<const float4*>(sr + ci));
+        v.x *= sm.x; v.y *= sm.y; v.z *= sm.z; v.w *= sm.w;
+        float4 w0 = __ldg(reinterpret_cast<const float4*>(wrgb + ci));
+        float4 w1 = __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci));
+        float4 w2 = __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci));
+        a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+        a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+        a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+      }
+    }
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (ok && ll < 3) {
+      const int c = ll;
+      float v = c == 0 ? a0 : (c == 1 ? a1 : a2);
+      if (pixw) v *= __ldg(pixw + (int64_t)b * pixw_sb + (int64_t)sy * lab_w + sx);
+      float* o = rgb + ((int64_t)b * 3 + c) * hw + (int64_t)y * w + xx;
+      if (accumulate) {
+        *o += v;
+      } else {
+        if (bias) v += __ldg(bias + c);
+        if (skip) {  // Upsample: zero-insert x2, pad (2,1), correlate with the flipped 4x4 FIR
+          const int sh = h >> 1, sw = w >> 1;
+          const float* sp = skip + ((int64_t)b * 3 + c) * sh * sw;
+          float u = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky) {
+            int uy = y - 2 + ky;
+            if (uy < 0 || (uy & 1) || (uy >> 1) >= sh) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              int ux = xx - 2 + kx;
+              if (ux < 0 || (ux & 1) || (ux >> 1) >= sw) continue;
+              u = fmaf(__ldg(sp + (int64_t)(uy >> 1) * sw + (ux >> 1)), __ldg(fir + (3 - ky) * 4 + (3 - kx)), u);
+            }
+          }
+          v += u;
+        }
+        *o = v;
+      }
+    }
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int block, int per_thread = 1) {
+  int64_t g = ceil_div64(n, (int64_t)block * per_thread);
+  const int64_t cap = 148 * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace e4s
+
+using namespace e4s;
+
+extern "C" int e4s_nchw_to_nhwc_f32(const float* x, float* y, int batch, int c, int h, int w, int c_pad, void* stream) {
+  E4S_REQUIRE(x && y && batch > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c, "nchw_to_nhwc: bad args");
+  int hw = h * w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c_pad, 32), batch);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, y, c, hw, c_pad);
+  return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int e4s_nhwc_to_nchw_f32(const float* x, int64_t x_pitch, float* y, int batch, int c, int h, int w, void* stream) {
+  E4S_REQUIRE(x && y && batch > 0 && c > 0 && h > 0 && w > 0 && x_pitch >= c, "nhwc_to_nchw: bad args");
+  int hw = h * w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), batch);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, x_pitch, y, c, hw);
+  return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int e4s_upfirdn2d_f32(const float* x, const float* kernel, float* out, int64_t planes, int in_h, int in_w,
+                                 int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                                 int pad_y0, int pad_y1, void* stream) {
+  E4S_REQUIRE(x && kernel && out, "upfirdn2d: null pointer");
+  E4S_REQUIRE(planes > 0 && in_h > 0 && in_w > 0 && kh > 0 && kw > 0, "upfirdn2d: bad shape");
+  E4S_REQUIRE(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0, "upfirdn2d: bad up/down");
+  // same shape rule as upfirdn2d_kernel.cu:167-168 of the reference
+  const int out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) / down_y;
+  const int out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) / down_x;
+  E4S_REQUIRE(out_h > 0 && out_w > 0, "upfirdn2d: empty output (%d x %d)", out_h, out_w);
+  cudaStream_t s = as_stream(stream);
+  const bool tiled = down_x == 1 && down_y == 1 && up_x == up_y && (up_x == 1 || up_x == 2) && kh <= 4 && kw <= 4 &&
+                     planes <= 65535;
+  if (tiled) {
+    dim3 grid(ceil_div(out_w, 64), ceil_div(out_h, 16), (unsigned)planes);
+    if (up_x == 1)
+      upfirdn2d_tile_kernel<1><<<grid, 256, 0, s>>>(x, kernel, out, in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0);
+    else
+      upfirdn2d_tile_kernel<2><<<grid, 256, 0, s>>>(x, kernel, out, in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0);
+  } else {
+    int64_t total = planes * out_h * out_w;
+    upfirdn2d_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, kernel, out, total, in_h, in_w, out_h, out_w, kh, kw,
+                                                                 up_x, up_y, down_x, down_y, pad_x0, pad_y0);
+  }
+  return check_launch("upfirdn2d");
+}
+
+extern "C" int e4s_bias_act_f32(const float* x, const float* bias, float* y, int64_t n, int64_t inner, int channels,
+                                float slope, float scale, void* stream) {
+  E4S_REQUIRE(x && y && n > 0 && inner > 0 && channels > 0, "bias_act: bad args");
+  cudaStream_t s = as_stream(stream);
+  const bool vec = (inner % 4 == 0) && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec)
+    bias_act_vec4_kernel<<<grid_for(n / 4, 256, 2), 256, 0, s>>>(reinterpret_cast<const float4*>(x), bias,
+                                                                 reinterpret_cast<float4*>(y), n / 4, inner / 4, channels,
+                                                                 slope, scale);
+  else
+    bias_act_kernel<<<grid_for(n, 256, 4), 256, 0, s>>>(x, bias, y, n, inner, channels, slope, scale);
+  return check_launch("bias_act");
+}
+
+extern "C" int e4s_noise_bias_act_nhwc_f32(float* x, int batch, int h, int w, int c, const float* noise,
+                                           const float* noise_w, int64_t noise_sb, int64_t noise_sc, const float* bias,
+                                           float slope, float scale, void* stream) {
+  E4S_REQUIRE(x && batch > 0 && h > 0 && w > 0 && c > 0, "noise_bias_act: bad args");
+  E4S_REQUIRE(!noise || noise_w, "noise_bias_act: noise without weight");
+  int64_t total = (int64_t)batch * h * w * c;
+  noise_bias_act_nhwc_kernel<<<grid_for(total, 256, 4), 256, 0, as_stream(stream)>>>(x, total, h * w, w, c, noise, noise_w,
+                                                                                     noise_sb, noise_sc, bias, slope, scale);
+  return check_launch("noise_bias_act");
+}
+
+extern "C" int e4s_mask_labels(const float* mask, int batch, int k, int h, int w, uint8_t* labels, int32_t* flags,
+                               void* stream) {
+  E4S_REQUIRE(mask && labels && flags && batch > 0 && k > 0 && k < 255 && h > 0 && w > 0, "mask_labels: bad args");
+  int64_t hw = (int64_t)h * w, total = hw * batch;
+  mask_labels_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(mask, k, hw, total, labels, flags);
+  return check_launch("mask_labels");
+}
+
+extern "C" int e4s_labels_to_onehot_f32(const uint8_t* labels, int batch, int k, int h, int w, float* onehot, void* stream) {
+  E4S_REQUIRE(labels && onehot && batch > 0 && k > 0 && h > 0 && w > 0, "labels_to_onehot: bad args");
+  int64_t hw = (int64_t)h * w, total = hw * batch * k;
+  labels_to_onehot_kernel<<<grid_for(total, 256, 2), 256, 0, as_stream(stream)>>>(labels, k, hw, total, onehot);
+  return check_launch("labels_to_onehot");
+}
+
+extern "C" int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, int w, int cin, const float* smod, const float* wrgb,
+                             const uint8_t* labels, int regions, int lab_h, int lab_w, const float* pixw, int64_t pixw_sb,
+                             const float* bias, const float* skip, const float* fir, float* rgb, int accumulate,
+                             void* stream) {
+  E4S_REQUIRE(x && smod && wrgb && rgb && batch > 0 && h > 0 && w > 0, "torgb: bad args");
+  E4S_REQUIRE(cin >= 8 && cin % 4 == 0 && x_pitch % 4 == 0, "torgb: cin/x_pitch must be multiples of 4");
+  E4S_REQUIRE(!skip || (fir && h % 2 == 0 && w % 2 == 0), "torgb: skip needs fir and even size");
+  E4S_REQUIRE(regions > 0 && (!(labels || pixw) || (lab_h > 0 && lab_w > 0)), "torgb: bad region args");
+  int64_t npix = (int64_t)batch * h * w;
+  cudaStream_t s = as_stream(stream);
+  if (cin >= 128) {
+    torgb_kernel<32><<<grid_for(npix, 256 / 32), 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
+                                                              pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
+  } else if (cin >= 32) {
+    torgb_kernel<8><<<grid_for(npix, 256 / 8), 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
+                                                            pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
+  } else {
+    torgb_kernel<4><<<grid_for(npix, 256 / 4), 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
+                                                            pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
+  }
+  return check_launch("torgb");
+}

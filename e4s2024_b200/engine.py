@@ -1,0 +1,245 @@
+"""Host-side launch helpers shared by the drop-in modules: weight packing, the conv launcher
+(fills `struct E4SConv`), and the per-forward region context built from the mask.
+
+Activations inside the engine are fp32 NHWC tensors [B,H,W,P] (P = pixel pitch >= channels);
+the nn.Module boundary stays NCHW like the reference.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+# engine selection for eligible convolutions: "tc" (tcgen05 bf16x3) or "f32" (CUDA-core fp32)
+_ENGINE = os.environ.get("E4S_CONV_ENGINE", "tc")
+
+
+def set_conv_engine(name: str):
+    global _ENGINE
+    assert name in ("tc", "f32")
+    _ENGINE = name
+
+
+def conv_engine() -> str:
+    return _ENGINE
+
+
+def pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+@dataclass
+class PackedConv:
+    """Weights in the e4s_conv_f32 layout [phases, K, cout_pad] (+ optional tensor-core image)."""
+    w: torch.Tensor
+    cin: int
+    cout: int
+    cout_pad: int
+    kh: int
+    kw: int
+    phases: int = 1
+    tc: Optional[torch.Tensor] = None
+
+    @property
+    def k(self) -> int:
+        return self.kh * self.kw * self.cin
+
+
+def tc_eligible(cin: int, cout: int) -> bool:
+    return cin % 64 == 0 and cout % 16 == 0 and cout >= 32
+
+
+def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, phases: int, want_tc: bool) -> PackedConv:
+    cout_pad = pad_to(cout, 4)
+    if cout_pad != cout:
+        w_pkc = torch.nn.functional.pad(w_pkc, (0, cout_pad - cout))
+    w_pkc = w_pkc.contiguous().float()
+    pc = PackedConv(w_pkc, cin, cout, cout_pad, kh, kw, phases)
+    if want_tc and w_pkc.is_cuda and tc_eligible(cin, cout):
+        pc.tc = L.pack_weights_tc(w_pkc, phases, pc.k, cout, cout_pad)
+    return pc
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, want_tc: bool = True) -> PackedConv:
+    """w [Co,Ci,kh,kw] -> k = (ky*kw + kx)*Ci_pad + ci rows, co contiguous."""
+    co, ci, kh, kw = w.shape
+    cin = ci if cin_pad is None else cin_pad
+    t = w.detach().permute(2, 3, 1, 0)                      # [kh,kw,Ci,Co]
+    if cin != ci:
+        t = torch.nn.functional.pad(t, (0, 0, 0, cin - ci))
+    return _finish_pack(t.reshape(1, kh * kw * cin, co), cin, co, kh, kw, 1, want_tc)
+
+
+def pack_linear_weight(w: torch.Tensor, want_tc: bool = False) -> PackedConv:
+    """w [out,in] (F.linear) as a 1x1 conv."""
+    return pack_conv_weight(w.detach()[:, :, None, None], want_tc=want_tc)
+
+
+def polyphase_weights(w: torch.Tensor, fir: torch.Tensor) -> torch.Tensor:
+    """conv_transpose2d(stride 2, weight w[Co,Ci,3,3] used as [Ci,Co,3,3]) followed by upfirdn2d(fir 4x4, pad=(1,1))
+    == four 3x3 phase filters applied at input resolution (re-derived):
+      out[2A+py, 2B+px] = sum_{u,v} x[A-1+u, B-1+v] * Wph[py,px,u,v]
+      Wph[py,px,u,v] = sum_{m,n} w[ky,kx] * fir_flipped[m,n],  ky = 2(1-u)+py+m-1, kx likewise, 0<=ky,kx<=2.
+    Returns [2,2,3,3,Ci,Co]."""
+    co, ci = w.shape[:2]
+    kf = torch.flip(fir.to(w.dtype), [0, 1])
+    out = w.new_zeros(2, 2, 3, 3, ci, co)
+    for py in range(2):
+        for u in range(3):
+            for m in range(4):
+                ky = 2 * (1 - u) + py + m - 1
+                if not 0 <= ky <= 2:
+                    continue
+                for px in range(2):
+                    for v in range(3):
+                        for n in range(4):
+                            kx = 2 * (1 - v) + px + n - 1
+                            if 0 <= kx <= 2:
+                                out[py, px, u, v] += w[:, :, ky, kx].t() * kf[m, n]
+    return out
+
+
+def pack_up_weight(w: torch.Tensor, fir: torch.Tensor, want_tc: bool = True) -> PackedConv:
+    co, ci = w.shape[:2]
+    ph = polyphase_weights(w.detach(), fir)                 # [2,2,3,3,Ci,Co]
+    return _finish_pack(ph.reshape(4, 9 * ci, co), ci, co, 3, 3, 4, want_tc)
+
+
+class View:
+    """An NHWC activation: tensor [B,H,W,P] + channel window [coff, coff+c)."""
+    __slots__ = ("t", "c", "coff")
+
+    def __init__(self, t: torch.Tensor, c: Optional[int] = None, coff: int = 0):
+        assert t.dim() == 4 and t.is_contiguous() and t.dtype == torch.float32
+        self.t, self.coff = t, coff
+        self.c = t.shape[3] - coff if c is None else c
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 4 * self.coff
+
+    @property
+    def pitch(self) -> int:
+        return self.t.shape[3]
+
+    @property
+    def bhw(self) -> Tuple[int, int, int]:
+        return self.t.shape[0], self.t.shape[1], self.t.shape[2]
+
+
+def new_nhwc(b, h, w, c, device) -> torch.Tensor:
+    return torch.empty(b, h, w, c, device=device, dtype=torch.float32)
+
+
+def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, in_stats=None, in_square=False,
+         smod=None, demod=None, labels=None, regions=1, smod_off=0, demod_off=0, pixw=None, ch_scale=None, ch_shift=None,
+         noise=None, noise_w=None, res: Optional[View] = None, res_after_act=False, act=L.ACT_NONE, slope=0.0, gain=1.0,
+         prelu=None, out: Optional[View] = None, accumulate=False, engine: Optional[str] = None) -> View:
+    """Launch one fused convolution (see struct E4SConv).  Returns the output view."""
+    b, hin, win = x.bhw
+    assert x.c == pw.cin, (x.c, pw.cin)
+    pad = (pw.kh // 2) if pad is None else pad
+    if up2:
+        hout, wout = 2 * hin, 2 * win
+    else:
+        hv, wv = hin << in_shift, win << in_shift
+        hout = (hv + 2 * pad - pw.kh) // stride + 1
+        wout = (wv + 2 * pad - pw.kw) // stride + 1
+    if out is None:
+        out = View(new_nhwc(b, hout, wout, pw.cout, x.t.device))
+    assert out.bhw == (b, hout, wout) and out.c == pw.cout, (out.bhw, (b, hout, wout), out.c, pw.cout)
+    p = L.E4SConv()
+    p.x, p.x_pitch = x.ptr, x.pitch
+    p.batch, p.hin, p.win, p.cin = b, hin, win, pw.cin
+    p.in_shift, p.in_square = in_shift, int(in_square)
+    p.w = pw.w.data_ptr()
+    p.cout, p.cout_pad = pw.cout, pw.cout_pad
+    p.kh, p.kw, p.stride, p.pad = pw.kh, pw.kw, stride, pad
+    p.mode = L.CONV_UP2 if up2 else L.CONV_NORMAL
+    p.hout, p.wout = hout, wout
+    if in_stats is not None:
+        p.in_mean, p.in_rstd = in_stats[0].data_ptr(), in_stats[1].data_ptr()
+    p.regions = regions
+    if smod is not None:
+        p.smod = smod.data_ptr() + 4 * smod_off
+    if demod is not None:
+        p.demod = demod.data_ptr() + 4 * demod_off
+    if labels is not None:
+        p.labels = labels.data_ptr()
+        p.lab_h, p.lab_w = labels.shape[1], labels.shape[2]
+    if pixw is not None:                                   # (tensor [B,K,Hm,Wm], region index)
+        m, ridx = pixw
+        p.pixw = m.data_ptr() + 4 * ridx * m.shape[2] * m.shape[3]
+        p.pixw_sb = m.shape[1] * m.shape[2] * m.shape[3]
+        p.lab_h, p.lab_w = m.shape[2], m.shape[3]
+    if ch_scale is not None:
+        p.ch_scale = ch_scale.data_ptr()
+    if ch_shift is not None:
+        p.ch_shift = ch_shift.data_ptr()
+    if noise is not None:
+        nb, nc, nh, nw_ = noise.shape
+        assert (nh, nw_) == (hout, wout) and nb in (1, b) and nc in (1, pw.cout) and noise.is_contiguous(), noise.shape
+        p.noise, p.noise_w = noise.data_ptr(), noise_w.data_ptr()
+        p.noise_sb = 0 if nb == 1 else nc * nh * nw_
+        p.noise_sc = 0 if nc == 1 else nh * nw_
+    if res is not None:
+        assert res.bhw == (b, hout, wout)
+        p.res, p.res_pitch, p.res_after_act = res.ptr, res.pitch, int(res_after_act)
+    p.act, p.act_slope, p.act_gain = act, slope, gain
+    if prelu is not None:
+        p.act_prelu = prelu.data_ptr()
+    p.out, p.out_pitch, p.accumulate = out.ptr, out.pitch, int(accumulate)
+    eng = engine or _ENGINE
+    use_tc = eng == "tc" and pw.tc is not None
+    L.conv(p, pw.tc if use_tc else None)
+    return out
+
+
+def linear_rows(x_ptr_tensor: torch.Tensor, rows: int, row_stride: int, offset: int, pw: PackedConv, bias=None,
+                act=L.ACT_NONE, slope=0.0, gain=1.0, in_square=False, out: Optional[torch.Tensor] = None,
+                engine: Optional[str] = None) -> torch.Tensor:
+    """y[r,:] = act(W x[r,:] + bias) for `rows` vectors of length pw.cin starting at element `offset`
+    of `x_ptr_tensor`, consecutive rows `row_stride` elements apart (all in floats)."""
+    dev = x_ptr_tensor.device
+    if out is None:
+        out = torch.empty(rows, pw.cout, device=dev, dtype=torch.float32)
+    p = L.E4SConv()
+    p.x, p.x_pitch = x_ptr_tensor.data_ptr() + 4 * offset, row_stride
+    p.batch, p.hin, p.win, p.cin = rows, 1, 1, pw.cin
+    p.in_square = int(in_square)
+    p.w = pw.w.data_ptr()
+    p.cout, p.cout_pad = pw.cout, pw.cout_pad
+    p.kh = p.kw = p.stride = 1
+    p.pad, p.mode = 0, L.CONV_NORMAL
+    p.hout = p.wout = 1
+    p.regions = 1
+    if bias is not None:
+        p.ch_shift = bias.data_ptr()
+    p.act, p.act_slope, p.act_gain = act, slope, gain
+    p.out, p.out_pitch = out.data_ptr(), out.stride(0)
+    eng = engine or "f32"
+    L.conv(p, pw.tc if (eng == "tc" and pw.tc is not None) else None)
+    return out
+
+
+class RegionCtx:
+    """Per-forward view of the mask [B,K,Hm,Wm]: u8 label map when every pixel has at most one
+    region with weight exactly 1 (the pipelines' one-hot masks), else the generic float path."""
+
+    def __init__(self, mask: torch.Tensor):
+        if mask.dim() != 4:
+            raise L.E4SError("mask must be [B,K,H,W]")
+        self.mask = mask.contiguous().float()
+        self.k = mask.shape[1]
+        self.labels, flags = L.mask_labels(self.mask)
+        self.onehot = int(flags.item()) == 0          # 4-byte D2H read, once per forward
+        self.regions = self.k
+
+    @property
+    def lab_hw(self):
+        return self.labels.shape[1], self.labels.shape[2]

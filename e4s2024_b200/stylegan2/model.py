@@ -1,0 +1,452 @@
+"""Mask-guided StyleGAN2 generator -- drop-in for the reference `models/stylegan2/model.py`
+(Generator side: :14-53, :78-94, :135-169, :184-698).  Same class names, constructor
+signatures, forward() signatures, return tuples and state_dict keys; the computation is the
+B200 engine (fused gather -> modulate -> GEMM -> demod/noise/bias/act epilogue), NHWC inside.
+
+What changed structurally versus the reference (results identical within fp32 tolerance):
+  * one fused convolution per layer instead of K = 12 grouped convolutions + mask-multiply-adds:
+    output pixel p is computed once with the style of ITS region r(p)  (exact for one-hot masks;
+    soft / overlapping masks take a per-region accumulate path on the same kernels);
+  * conv_transpose2d(stride 2) + Blur is folded into four 3x3 phase filters (engine.polyphase_weights);
+  * per-sample weights are never materialised: modulation scales the gathered activations,
+    demodulation is a per-(sample, region, channel) epilogue scale;
+  * noise, bias, leaky-ReLU*sqrt(2) run in the conv epilogue; ToRGB fuses bias and the FIR-upsampled skip.
+Forward only (inference hot path); Discriminator / ConvLayer / ResBlock are training-only and not provided.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import engine as E
+from ..engine import View
+from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+
+SQRT2 = 2 ** 0.5
+
+
+class PixelNorm(nn.Module):
+    def forward(self, input):
+        return input * torch.rsqrt(torch.mean(input ** 2, dim=1, keepdim=True) + 1e-8)
+
+
+def make_kernel(k):
+    k = torch.tensor(k, dtype=torch.float32)
+    if k.ndim == 1:
+        k = k[None, :] * k[:, None]
+    k /= k.sum()
+    return k
+
+
+class Upsample(nn.Module):
+    """model.py:34-53."""
+
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        kernel = make_kernel(kernel) * (factor ** 2)
+        self.register_buffer("kernel", kernel)
+        p = kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Blur(nn.Module):
+    """model.py:78-94."""
+
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        kernel = make_kernel(kernel)
+        if upsample_factor > 1:
+            kernel = kernel * (upsample_factor ** 2)
+        self.register_buffer("kernel", kernel)
+        self.pad = pad
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, pad=self.pad)
+
+
+def _ver(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+class EqualLinear(nn.Module):
+    """model.py:135-169."""
+
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+        self._pack = None
+
+    def packed(self):
+        key = _ver(self.weight) + (_ver(self.bias) if self.bias is not None else ())
+        if self._pack is None or self._pack[0] != key:
+            pw = E.pack_linear_weight(self.weight.detach() * self.scale)
+            b = None if self.bias is None else (self.bias.detach() * self.lr_mul).contiguous()
+            self._pack = (key, pw, b)
+        return self._pack[1], self._pack[2]
+
+    def rows(self, src: torch.Tensor, rows: int, row_stride: int, offset: int) -> torch.Tensor:
+        pw, b = self.packed()
+        if self.activation:
+            return E.linear_rows(src, rows, row_stride, offset, pw, bias=b, act=L.ACT_LRELU, slope=0.2, gain=SQRT2)
+        return E.linear_rows(src, rows, row_stride, offset, pw, bias=b)
+
+    def forward(self, input):
+        x = input.contiguous().float()
+        lead = x.shape[:-1]
+        y = self.rows(x, x.numel() // x.shape[-1], x.shape[-1], 0)
+        return y.reshape(*lead, -1)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
+
+
+class StyleRows:
+    """`rows` style vectors of length 512 inside a contiguous tensor: row r starts at offset + r*stride."""
+    __slots__ = ("t", "rows", "stride", "offset", "regions")
+
+    def __init__(self, t, rows, stride, offset, regions):
+        self.t, self.rows, self.stride, self.offset, self.regions = t, rows, stride, offset, regions
+
+    @staticmethod
+    def from_tensor(style: torch.Tensor) -> "StyleRows":
+        s = style.contiguous().float()
+        if s.dim() == 2:
+            return StyleRows(s, s.shape[0], s.shape[1], 0, 1)
+        assert s.dim() == 3
+        return StyleRows(s, s.shape[0] * s.shape[1], s.shape[2], 0, s.shape[1])
+
+
+class ModulatedConv2d(nn.Module):
+    """model.py:184-320."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
+                 downsample=False, blur_kernel=[1, 3, 3, 1], fused=True):
+        super().__init__()
+        self.eps = 1e-8
+        self.kernel_size = kernel_size
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = upsample
+        self.downsample = downsample
+        if upsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) - (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2 + factor - 1, p // 2 + 1), upsample_factor=factor)
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2, p // 2))
+        fan_in = in_channel * kernel_size ** 2
+        self.scale = 1 / math.sqrt(fan_in)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.demodulate = demodulate
+        self.fused = fused
+        self._pack = None
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
+                f"upsample={self.upsample}, downsample={self.downsample})")
+
+    # ---- packed weights (rebuilt when the parameters change, e.g. after PTI fine-tuning) ----------
+    def packed(self):
+        key = _ver(self.weight) + ((_ver(self.blur.kernel)) if self.upsample else ())
+        if self._pack is None or self._pack[0] != key:
+            w = (self.weight.detach()[0] * self.scale).float()                    # [Co,Ci,k,k]
+            if self.upsample:
+                if self.kernel_size != 3 or tuple(self.blur.kernel.shape) != (4, 4) or self.blur.pad != (1, 1):
+                    raise L.E4SError("up-sampling ModulatedConv2d supports kernel_size=3 with a 4-tap blur")
+                conv = E.pack_up_weight(w, self.blur.kernel.detach().to(w.device))
+            else:
+                conv = E.pack_conv_weight(w)
+            wsq = None
+            if self.demodulate:                                                   # sum_taps (scale*W)^2 -> [Ci] x [Co]
+                wsq = E.pack_conv_weight(w.pow(2).sum(dim=(2, 3))[:, :, None, None], want_tc=False)
+            self._pack = (key, conv, wsq)
+        return self._pack[1], self._pack[2]
+
+    def tables(self, st: StyleRows):
+        """s[row, ci] = modulation(style) (model.py:276); d[row, co] = rsqrt(sum (scale*W*s)^2 + eps) (:279-281)."""
+        _, wsq = self.packed()
+        s = self.modulation.rows(st.t, st.rows, st.stride, st.offset)
+        d = None
+        if self.demodulate:
+            d = E.linear_rows(s, st.rows, self.in_channel, 0, wsq, act=L.ACT_RSQRT_EPS, slope=self.eps, in_square=True)
+        return s, d
+
+    def run(self, x: View, st: StyleRows, ctx: Optional[E.RegionCtx], **epilogue) -> View:
+        """Fused modulated convolution on an NHWC view; `epilogue` = noise/bias/activation kwargs of engine.conv."""
+        if self.downsample:
+            raise NotImplementedError("downsample=True is only used by the (training-only) Discriminator")
+        conv, _ = self.packed()
+        s, d = self.tables(st)
+        regional = st.regions > 1
+        if regional and ctx is None:
+            raise L.E4SError("regional styles need a mask")
+        if not regional or ctx.onehot:
+            return E.conv(x, conv, up2=self.upsample, smod=s, demod=d, regions=st.regions,
+                          labels=ctx.labels if regional else None, **epilogue)
+        # generic float masks: sum_k mask_k * conv(x; style_k), then the epilogue (model.py:395-398)
+        out = None
+        for r in range(st.regions):
+            out = E.conv(x, conv, up2=self.upsample, smod=s, demod=d, regions=st.regions, smod_off=r * self.in_channel,
+                         demod_off=r * self.out_channel, pixw=(ctx.mask, r), out=out, accumulate=r > 0)
+        if epilogue:
+            b, h, w = out.bhw
+            noise, nw = epilogue.get("noise"), epilogue.get("noise_w")
+            nsb = nsc = 0
+            if noise is not None:
+                nsb = 0 if noise.shape[0] == 1 else noise.shape[1] * h * w
+                nsc = 0 if noise.shape[1] == 1 else h * w
+            L.noise_bias_act_nhwc(out.t, noise, nw, nsb, nsc, epilogue.get("ch_shift"), epilogue.get("slope", 1.0),
+                                  epilogue.get("gain", 1.0))
+        return out
+
+    def forward(self, input, style):
+        x = View(L.nchw_to_nhwc(input.contiguous().float()))
+        out = self.run(x, StyleRows.from_tensor(style), None)
+        return L.nhwc_to_nchw(out.t)
+
+
+class NoiseInjection(nn.Module):
+    """model.py:323-335 (standalone form; inside StyledConv the add happens in the conv epilogue)."""
+
+    def __init__(self):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1))
+
+    def forward(self, image, noise=None):
+        if noise is None:
+            batch, _, height, width = image.shape
+            noise = image.new_empty(batch, 1, height, width).normal_()
+        return image + self.weight * noise
+
+
+class ConstantInput(nn.Module):
+    """model.py:338-348."""
+
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)
+
+
+def _noise_for(noise, b, h, w, device):
+    if noise is None:                                   # model.py:329-333: fresh N(0,1) per call
+        return torch.empty(b, 1, h, w, device=device, dtype=torch.float32).normal_()
+    return noise.detach().to(device).contiguous().float()
+
+
+class StyledConv(nn.Module):
+    """model.py:351-423."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False, blur_kernel=[1, 3, 3, 1],
+                 demodulate=True, mask_op=False):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim, upsample=upsample,
+                                    blur_kernel=blur_kernel, demodulate=demodulate)
+        self.noise = NoiseInjection()
+        self.activate = FusedLeakyReLU(out_channel)
+        self.mask_op = mask_op
+
+    def run(self, x: View, st: StyleRows, ctx, noise) -> View:
+        b, h, w = x.bhw
+        if self.conv.upsample:
+            h, w = 2 * h, 2 * w
+        nz = _noise_for(noise, b, h, w, x.t.device)
+        return self.conv.run(x, st, ctx if self.mask_op else None, noise=nz, noise_w=self.noise.weight.detach(),
+                             ch_shift=self.activate.bias.detach(), act=L.ACT_LRELU,
+                             slope=self.activate.negative_slope, gain=self.activate.scale)
+
+    def forward(self, input, style, mask, noise=None):
+        x = View(L.nchw_to_nhwc(input.contiguous().float()))
+        ctx = E.RegionCtx(mask) if self.mask_op else None
+        return L.nhwc_to_nchw(self.run(x, StyleRows.from_tensor(style), ctx, noise).t)
+
+
+class ToRGB(nn.Module):
+    """model.py:426-479."""
+
+    def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=[1, 3, 3, 1], mask_op=False):
+        super().__init__()
+        if upsample:
+            self.upsample = Upsample(blur_kernel)
+        self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
+        self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+        self.mask_op = mask_op
+        self._wrgb = None
+
+    def _weights(self):
+        key = _ver(self.conv.weight)
+        if self._wrgb is None or self._wrgb[0] != key:
+            w = (self.conv.weight.detach()[0, :, :, 0, 0] * self.conv.scale).contiguous().float()    # [3,Ci]
+            self._wrgb = (key, w)
+        return self._wrgb[1]
+
+    def run(self, x: View, st: StyleRows, ctx, skip: Optional[torch.Tensor]) -> torch.Tensor:
+        """x NHWC view, skip NCHW [B,3,H/2,W/2] or None -> rgb NCHW [B,3,H,W]."""
+        b, h, w = x.bhw
+        s = self.conv.modulation.rows(st.t, st.rows, st.stride, st.offset)
+        rgb = torch.empty(b, 3, h, w, device=x.t.device, dtype=torch.float32)
+        fir = None
+        if skip is not None:
+            fir = self.upsample.kernel
+            if tuple(fir.shape) != (4, 4) or self.upsample.pad != (2, 1):
+                raise L.E4SError("ToRGB skip path supports the 4-tap FIR (pad=(2,1)) only")
+            skip = skip.contiguous().float()
+            assert skip.shape == (b, 3, h // 2, w // 2), skip.shape
+        bias = self.bias.detach().reshape(3).contiguous()
+        regional = self.mask_op and st.regions > 1
+        xin = View(x.t, x.c, x.coff)
+        if not regional:
+            L.torgb(xin.t, x.c, s, self._weights(), None, st.regions, (0, 0), None, 0, bias, skip, fir, rgb, False)
+        elif ctx.onehot:
+            L.torgb(xin.t, x.c, s, self._weights(), ctx.labels, st.regions, ctx.lab_hw, None, 0, bias, skip, fir, rgb, False)
+        else:
+            m = ctx.mask
+            plane = m.shape[2] * m.shape[3]
+            for r in range(st.regions):
+                L.torgb(xin.t, x.c, s[r:], self._weights(), None, st.regions, ctx.lab_hw, m.data_ptr() + 4 * r * plane,
+                        m.shape[1] * plane, bias, skip, fir, rgb, r > 0)
+        return rgb
+
+    def forward(self, input, style, mask, skip=None):
+        x = View(L.nchw_to_nhwc(input.contiguous().float()))
+        st = StyleRows.from_tensor(style)
+        ctx = E.RegionCtx(mask) if (self.mask_op and st.regions > 1) else None
+        return self.run(x, st, ctx, skip)
+
+
+class Generator(nn.Module):
+    """model.py:482-698."""
+
+    def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01,
+                 split_layer_idx=7, remaining_layer_idx=18):
+        super().__init__()
+        self.split_layer_idx = split_layer_idx
+        self.remaining_layer_idx = remaining_layer_idx
+        self.size = size
+        self.style_dim = style_dim
+        layers = [PixelNorm()]
+        for _ in range(n_mlp):
+            layers.append(EqualLinear(style_dim, style_dim, lr_mul=lr_mlp, activation="fused_lrelu"))
+        self.style = nn.Sequential(*layers)
+        self.channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * channel_multiplier, 128: 128 * channel_multiplier,
+                         256: 64 * channel_multiplier, 512: 32 * channel_multiplier, 1024: 16 * channel_multiplier}
+        self.input = ConstantInput(self.channels[4])
+        self.conv1 = StyledConv(self.channels[4], self.channels[4], 3, style_dim, blur_kernel=blur_kernel, mask_op=True)
+        self.to_rgb1 = ToRGB(self.channels[4], style_dim, upsample=False, mask_op=True)
+        self.log_size = int(math.log(size, 2))
+        self.num_layers = (self.log_size - 2) * 2 + 1
+        self.convs = nn.ModuleList()
+        self.upsamples = nn.ModuleList()
+        self.to_rgbs = nn.ModuleList()
+        self.noises = nn.Module()
+        in_channel = self.channels[4]
+        for layer_idx in range(self.num_layers):
+            res = (layer_idx + 5) // 2
+            self.noises.register_buffer(f"noise_{layer_idx}", torch.randn(1, 1, 2 ** res, 2 ** res))
+        rl = self.remaining_layer_idx
+        for i in range(3, self.log_size + 1):
+            out_channel = self.channels[2 ** i]
+            conv_masked = not (i > (2 + rl // 2))
+            self.convs.append(StyledConv(in_channel, out_channel, 3, style_dim, upsample=True, blur_kernel=blur_kernel,
+                                         mask_op=conv_masked))
+            self.convs.append(StyledConv(out_channel, out_channel, 3, style_dim, blur_kernel=blur_kernel,
+                                         mask_op=conv_masked))
+            self.to_rgbs.append(ToRGB(out_channel, style_dim, mask_op=not (rl != 17 and i >= (2 + rl // 2))))
+            in_channel = out_channel
+        self.n_latent = self.log_size * 2 - 2
+
+    def make_noise(self):
+        device = self.input.input.device
+        noises = [torch.randn(1, 1, 2 ** 2, 2 ** 2, device=device)]
+        for i in range(3, self.log_size + 1):
+            for _ in range(2):
+                noises.append(torch.randn(1, 1, 2 ** i, 2 ** i, device=device))
+        return noises
+
+    def mean_latent(self, n_latent):
+        latent_in = torch.randn(n_latent, self.style_dim, device=self.input.input.device)
+        return self.style(latent_in).mean(0, keepdim=True)
+
+    def get_latent(self, input):
+        return self.style(input)
+
+    @torch.no_grad()
+    def forward(self, styles, structure_feats, mask, return_latents=False, inject_index=None, truncation=1,
+                truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
+                use_structure_code=False):
+        if not input_is_latent:
+            styles = [self.style(s) for s in styles]
+        if noise is None:
+            noise = [None] * self.num_layers if randomize_noise else \
+                [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        if truncation < 1:
+            styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+        if len(styles) != 1 or styles[0].ndim != 4:
+            # model.py:642-659: the 2-/3-D and style-mixing branches index latent[:, :, i] and cannot run with
+            # regional styles in the reference either; only the [B,K,n_latent,512] form is meaningful.
+            raise L.E4SError("Generator expects styles=[latent] with latent of shape [B, K, n_latent, style_dim]")
+        latent = styles[0].contiguous().float()
+        b, k, nl, sd = latent.shape
+        if sd != self.style_dim or nl < self.n_latent:
+            raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
+        ctx = E.RegionCtx(mask.to(latent.device))
+        if ctx.k != k or ctx.mask.shape[0] != b:
+            raise L.E4SError("mask and latent disagree on batch / number of regions")
+
+        def regional(i):      # latent[:, :, i]
+            return StyleRows(latent, b * k, nl * sd, i * sd, k)
+
+        def glob(i):          # latent[:, 0, i]
+            return StyleRows(latent, b, k * nl * sd, i * sd, 1)
+
+        x = View(L.nchw_to_nhwc(self.input.input.detach().float().repeat(b, 1, 1, 1).contiguous()))
+        out = self.conv1.run(x, regional(0), ctx, noise[0])
+        skip = self.to_rgb1.run(out, regional(1), ctx, None)
+        intermediate_feats = None
+        rl = self.remaining_layer_idx
+        i = 1
+        for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
+                                                        self.to_rgbs):
+            if i < rl:
+                out = conv1.run(out, regional(i), ctx, noise1)
+                if i + 2 == self.split_layer_idx:
+                    if use_structure_code:
+                        out = View(L.nchw_to_nhwc(structure_feats.contiguous().float()))
+                    intermediate_feats = L.nhwc_to_nchw(out.t)
+                out = conv2.run(out, regional(i + 1), ctx, noise2)
+                st = regional(i + 2) if (rl == 17 or i + 2 != rl) else glob(i + 2)
+                skip = to_rgb.run(out, st, ctx, skip)
+            else:
+                out = conv1.run(out, glob(i), ctx, noise1)
+                out = conv2.run(out, glob(i + 1), ctx, noise2)
+                skip = to_rgb.run(out, glob(i + 2), ctx, skip)
+            i += 2
+        image = skip
+        if return_latents:
+            return image, latent, intermediate_feats
+        return image, None, intermediate_feats
+
+
+def generator_state_shapes(size: int, style_dim: int = 512, n_mlp: int = 8, **kw):
+    """{name: shape} of Generator.state_dict() without allocating it (tests / synthetic weights)."""
+    with torch.device("meta"):
+        g = Generator(size, style_dim, n_mlp, **kw)
+    return {k: tuple(v.shape) for k, v in g.state_dict().items()}

@@ -1,0 +1,31 @@
+"""Tensor helpers on either side of the hot path (reference: utils/torch_utils.py:64-76,207-223)."""
+import numpy as np
+import torch
+from PIL import Image
+
+from .. import _lib as L
+
+
+def labelMap2OneHot(label, num_cls):
+    """[bs,1,H,W] integer label map -> one-hot float [bs,num_cls,H,W] (torch_utils.py:207-213)."""
+    if label.is_cuda:
+        return L.labels_to_onehot(label[:, 0].to(torch.uint8).contiguous(), num_cls)
+    bs, _, h, w = label.size()
+    return torch.zeros(bs, num_cls, h, w).scatter_(1, label.long(), 1.0)
+
+
+def tensor2im(var, is_zero_center: bool = True):
+    """torch_utils.py:64-76."""
+    var = var.squeeze()
+    if var.ndim == 3:
+        var = var.permute(1, 2, 0)
+    var = var.cpu().detach().numpy()
+    if is_zero_center:
+        var = (var + 1) / 2
+    var = np.clip(var, 0, 1) * 255
+    return Image.fromarray(var.astype("uint8"))
+
+
+def remove_module_prefix(state_dict, prefix):
+    """torch_utils.py:216-223."""
+    return {k.replace(prefix, "", 1): v for k, v in state_dict.items()}

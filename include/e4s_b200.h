@@ -1,0 +1,196 @@
+/* e4s_b200.h -- C-ABI of the B200-native E4S hot path (libe4s_b200.so).
+ *
+ * Boundary contract:
+ *  - every function is extern "C", takes raw DEVICE pointers + int shapes + a cudaStream_t
+ *    (passed as void*), returns 0 on success or a negative E4S_ERR_* code; the message is
+ *    available from e4s_last_error() (thread-local).
+ *  - the caller owns every buffer (inputs, outputs, packed weights, workspaces); the library
+ *    never allocates, frees or retains caller memory.  All work is enqueued on `stream`
+ *    (CUDA-graph capturable); no host synchronisation inside.
+ *  - there is no CPU fallback: without a CUDA device every entry point fails.
+ *
+ * Which reference interface each entry point replaces (paths under the reference root):
+ *  e4s_upfirdn2d_f32      <- pybind `upfirdn2d(input,kernel,up_x,up_y,down_x,down_y,pad_x0,pad_x1,pad_y0,pad_y1)`
+ *                            models/stylegan2/op/upfirdn2d.cpp:12-23, kernel upfirdn2d_kernel.cu:52-137
+ *  e4s_bias_act_f32       <- pybind `fused_bias_act(input,bias,refer,act,grad,alpha,scale)`
+ *                            models/stylegan2/op/fused_bias_act.cpp:11-21, kernel fused_bias_act_kernel.cu:18-49
+ *  e4s_conv_f32 / e4s_conv_tc  <- torch F.conv2d / F.conv_transpose2d call sites of the path:
+ *                            models/stylegan2/op/conv2d_gradfix.py:34-42,66-75 (ModulatedConv2d, model.py:287-318),
+ *                            models/encoders/helpers.py:128-139, psp_encoders.py:334,
+ *                            swap_face_fine/face_parsing/model.py:23-35, resnet.py:17-49,62-64, F.linear model.py:156-162
+ *  e4s_torgb_f32          <- ToRGB.forward, models/stylegan2/model.py:439-479 (1x1 modconv + bias + Upsample(skip))
+ *  e4s_mask_labels        <- F.interpolate(mask,'nearest') region lookup, model.py:391,445; psp_encoders.py:357
+ *  e4s_chan_stats_f32     <- InstanceNorm2d statistics / AdaptiveAvgPool2d / F.avg_pool2d(full), helpers.py:60,128-138
+ *  e4s_vec_fc_f32         <- SEModule fc1/fc2 (helpers.py:61-71), conv_atten/conv_avg/FFM 1x1 on pooled vectors (model.py:86-88,117-118,208-213)
+ *  e4s_residual_combine_f32 <- bottleneck_IR_SE_Ours tail `res*gate + shortcut` (helpers.py:141-144), ARM/FFM gating (model.py:89,130,214-215)
+ *  e4s_masked_mean_f32    <- FSEncoder_PSP.get_per_comp_styleCode, psp_encoders.py:355-375
+ *  e4s_resize_bilinear_f32<- F.interpolate(img,(256,256),'bilinear') networks.py:114,217; BiSeNet head upsample model.py:257-259
+ *  e4s_maxpool3x3s2_f32   <- nn.MaxPool2d(3,2,1), resnet.py:66,75
+ *  e4s_upsample_argmax_u8 <- F.interpolate(...,align_corners=True) + torch.argmax + seg19->seg12 LUT,
+ *                            model.py:257, face_parsing_demo.py:170, datasets/dataset.py:58-108
+ *  e4s_bicubic_down_norm_f32 <- BicubicDownSample.forward + clamp + (x-mean)/std, face_parsing_demo.py:46-84,155
+ *  e4s_nchw_to_nhwc_f32 / e4s_nhwc_to_nchw_f32 <- layout adapters at the nn.Module boundary (API is NCHW)
+ */
+#ifndef E4S_B200_H
+#define E4S_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E4S_OK 0
+#define E4S_ERR_ARG (-1)      /* bad shape / alignment / null pointer */
+#define E4S_ERR_CUDA (-2)     /* CUDA runtime error (launch failure, no device) */
+#define E4S_ERR_UNSUPPORTED (-3)
+
+/* activation codes for E4SConv.act */
+enum { E4S_ACT_NONE = 0, E4S_ACT_LRELU = 1, E4S_ACT_RELU = 2, E4S_ACT_PRELU = 3, E4S_ACT_SIGMOID = 4,
+       E4S_ACT_RSQRT_EPS = 5 };
+/* E4SConv.mode */
+enum { E4S_CONV_NORMAL = 0, E4S_CONV_UP2_POLYPHASE = 1 };
+
+/* One convolution / GEMM launch.  Activations are fp32 NHWC with an arbitrary pixel pitch
+ * (so channel slices of wider buffers can be read / written).  GEMM view: M = B*Hout*Wout
+ * output pixels, N = cout, K = taps*cin with k = tap*cin + ci.
+ *
+ * A operand (gathered on the fly, never materialised):
+ *   a[p, tap, ci] = T( x[b, iy, ix, ci] ),  iy = oy*stride - pad + ky  (then >> in_shift: the conv
+ *   reads a nearest-upsampled view of x),  zero outside the image.
+ *   T applies, in order: InstanceNorm (v - in_mean[b,ci]) * in_rstd[b,ci]   (if in_mean)
+ *                        square v*v (if in_square; used for the demodulation table GEMM)
+ *                        style modulation v * smod[(b*regions + r(p))*cin + ci] (if smod)
+ *   r(p) = labels[b, floor(oy*lab_h/Hout), floor(ox*lab_w/Wout)]   (0 if labels == NULL)
+ * mode E4S_CONV_UP2_POLYPHASE: conv_transpose2d(stride 2) + 4x4 FIR folded into four 3x3 phase
+ *   filters; out pixel (2a+py, 2b+px) gathers x[a-1+u, b-1+v]; weights hold 4 phase matrices.
+ *
+ * Epilogue, in order:  v = acc * demod[(b*regions + r)*cout + n]      (if demod)
+ *                      v *= pixw[b*pixw_sb + sy*lab_w + sx]             (if pixw; generic float masks)
+ *                      v  = v * ch_scale[n]                             (if ch_scale)
+ *                      v += noise_w[0] * noise[b*noise_sb + n*noise_sc + oy*Wout + ox] (if noise)
+ *                      v += ch_shift[n]                                 (if ch_shift)
+ *                      v += res[pix*res_pitch + n]                      (if res && !res_after_act)
+ *                      v  = act(v)   LRELU: (v<0 ? v*act_slope : v)*act_gain; PRELU: slope = act_prelu[n];
+ *                                     RSQRT_EPS: rsqrt(v + act_slope)
+ *                      v += res[...]                                    (if res && res_after_act)
+ *                      out[pix*out_pitch + n] = v   (or += if accumulate)
+ */
+typedef struct E4SConv {
+  const float* x;   int64_t x_pitch;       /* floats per pixel of the input buffer */
+  int32_t batch, hin, win, cin;            /* cin % 8 == 0 */
+  int32_t in_shift;                        /* log2 nearest-upsample factor of the input view */
+  int32_t in_square;                       /* square the gathered value (after InstanceNorm) */
+  const float* w;                          /* packed weights, see e4s_conv_f32 / e4s_conv_tc */
+  int32_t cout, cout_pad;                  /* cout_pad % 4 == 0, row length of packed w */
+  int32_t kh, kw, stride, pad, mode;
+  int32_t hout, wout;
+  const float* in_mean; const float* in_rstd;          /* [batch, cin] or NULL */
+  const float* smod; const uint8_t* labels;            /* [batch, regions, cin]; [batch, lab_h, lab_w] */
+  int32_t regions, lab_h, lab_w;
+  const float* demod;                                  /* [batch, regions, cout] or NULL */
+  const float* pixw; int64_t pixw_sb;                  /* float mask plane(s), sampled like labels */
+  const float* ch_scale; const float* ch_shift;        /* [cout] or NULL */
+  const float* noise; const float* noise_w; int64_t noise_sb, noise_sc;
+  const float* res; int64_t res_pitch; int32_t res_after_act;
+  int32_t act; float act_slope, act_gain; const float* act_prelu;
+  float* out; int64_t out_pitch; int32_t accumulate;
+} E4SConv;
+
+const char* e4s_last_error(void);
+/* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
+int64_t e4s_launch_count(void);
+int e4s_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* sizeof(struct E4SConv) as compiled, so bindings can verify their mirror of the struct */
+int e4s_sizeof_conv(void);
+
+/* fp32 CUDA-core implicit GEMM.  w layout: [phase][K][cout_pad] (phase = 1 or 4). */
+int e4s_conv_f32(const E4SConv* p, void* stream);
+
+/* tcgen05 (5th-gen tensor core) implicit GEMM with the 3-pass bf16 hi/lo split (fp32 accumulate in TMEM).
+ * w points to the packed bf16 image produced by e4s_pack_weights_tc; cin % 64 == 0, cout % 16 == 0. */
+int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream);
+/* bytes needed for the packed tensor-core weights of a [phases, K, cout] fp32 matrix */
+int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);
+/* w_f32: [phases][K][cout_pad] (the e4s_conv_f32 layout) -> w_packed (hi/lo bf16, UMMA K-major SW128 tiles) */
+int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cout, int cout_pad, void* w_packed, void* stream);
+
+/* upfirdn2d on NCHW fp32 [planes, in_h, in_w] (planes = B*C). kernel [kh,kw] is correlated FLIPPED. */
+int e4s_upfirdn2d_f32(const float* x, const float* kernel, float* out, int64_t planes, int in_h, int in_w,
+                      int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* y[i] = lrelu(x[i] + bias[(i / inner) % channels], slope) * scale   (bias may be NULL) */
+int e4s_bias_act_f32(const float* x, const float* bias, float* y, int64_t n, int64_t inner, int channels,
+                     float slope, float scale, void* stream);
+
+/* NHWC noise+bias+leaky-relu for the generic-mask path: y = lrelu(x + nw*noise + bias[c]) * scale, in place ok */
+int e4s_noise_bias_act_nhwc_f32(float* x, int batch, int h, int w, int c, const float* noise, const float* noise_w,
+                                int64_t noise_sb, int64_t noise_sc, const float* bias, float slope, float scale,
+                                void* stream);
+
+int e4s_nchw_to_nhwc_f32(const float* x, float* y, int batch, int c, int h, int w, int c_pad, void* stream);
+int e4s_nhwc_to_nchw_f32(const float* x, int64_t x_pitch, float* y, int batch, int c, int h, int w, void* stream);
+
+/* mask [batch, k, h, w] float -> labels u8 [batch, h, w]: index of the single non-zero entry (which must
+ * equal 1).  flags[0] counts thread blocks that saw a pixel NOT of that form (soft, overlapping or empty
+ * masks) -> the caller must take the generic per-region path. */
+int e4s_mask_labels(const float* mask, int batch, int k, int h, int w, uint8_t* labels, int32_t* flags, void* stream);
+
+/* ToRGB: rgb[b,c,y,x] = sum_ci x[b,y,x,ci] * smod[(b*regions+r)*cin + ci] * wrgb[c*cin + ci] + bias[c] + up2(skip)[b,c,y,x]
+ * (wrgb = scale * weight[3,cin]; skip [batch,3,h/2,w/2] NCHW or NULL, 4x4 FIR `fir` as in Upsample: up=2, pad=(2,1)).
+ * pixw != NULL: multiply the dot product by the float mask (generic path); accumulate != 0 adds into rgb
+ * without bias/skip. */
+int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, int w, int cin, const float* smod, const float* wrgb,
+                  const uint8_t* labels, int regions, int lab_h, int lab_w, const float* pixw, int64_t pixw_sb,
+                  const float* bias, const float* skip, const float* fir, float* rgb, int accumulate, void* stream);
+
+/* per-(b,c) statistics of an NHWC tensor: mean, rstd = 1/sqrt(var_biased + eps) (either may be NULL).
+ * ws: workspace of e4s_chan_stats_ws_bytes(batch, c) bytes. Deterministic (fixed split, fp64 partials). */
+int64_t e4s_chan_stats_ws_bytes(int batch, int c);
+int e4s_chan_stats_f32(const float* x, int64_t x_pitch, int batch, int hw, int c, float eps, float* mean, float* rstd,
+                       void* ws, void* stream);
+
+/* y[b,o] = act( scale[o] * sum_i w[o*cin + i] * x[b*x_stride + i] + shift[o] )  -- tiny per-sample FC */
+int e4s_vec_fc_f32(const float* x, int64_t x_stride, const float* w, const float* scale, const float* shift,
+                   float* y, int batch, int cin, int cout, int act, void* stream);
+
+/* out[b,p,c] = T(a[b,p,c]) * gate[b,c] (+ T2(r[b, p', c]))   with
+ *   T  = (v - a_mean[b,c]) * a_rstd[b,c] if a_mean else v ;  gate == NULL -> 1 ; gate_plus_one -> v*gate + v
+ *   r [batch, r_h, r_w, r_pitch]: r_sub > 1 reads pixel (y*r_sub, x*r_sub) (MaxPool2d(1, stride) shortcut);
+ *   r_sub == 1 reads the legacy-nearest resize of r to h x w (identity when sizes match).
+ *   T2 normalises with r_mean/r_rstd if given.  Then relu (if set), then PReLU with slopes prelu[c] (if given). */
+int e4s_residual_combine_f32(const float* a, int64_t a_pitch, const float* a_mean, const float* a_rstd,
+                             const float* gate, int gate_plus_one, const float* r, int64_t r_pitch, int r_h, int r_w,
+                             int r_sub, const float* r_mean, const float* r_rstd, int relu, const float* prelu,
+                             float* out, int64_t out_pitch, int batch, int h, int w, int c, void* stream);
+
+/* codes[b, k, c_off + c] = mean over pixels with mask[b,k,sy,sx] != 0 of feat[b,y,x,c]; 0 if none */
+int e4s_masked_mean_f32(const float* feat, int64_t f_pitch, int batch, int h, int w, int c, const float* mask, int k,
+                        int mh, int mw, float* codes, int64_t codes_stride_b, int64_t codes_stride_k, int c_off,
+                        void* stream);
+
+/* bilinear resize NCHW -> NHWC (c_pad channels, zero filled) or NHWC->NCHW; align_corners as torch */
+int e4s_resize_bilinear_nchw_to_nhwc_f32(const float* x, int batch, int c, int hin, int win, float* y, int hout,
+                                         int wout, int c_pad, int align_corners, void* stream);
+int e4s_resize_bilinear_nhwc_to_nchw_f32(const float* x, int64_t x_pitch, int batch, int c, int hin, int win, float* y,
+                                         int hout, int wout, int align_corners, void* stream);
+int e4s_maxpool3x3s2_nhwc_f32(const float* x, int batch, int h, int w, int c, float* y, void* stream);
+
+/* logits NHWC [batch, hin, win, pitch] (first c channels) -> bilinear(align_corners=True) upsample to
+ * hout x wout, argmax over c (lowest index wins ties), optional 256-entry LUT; labels u8 [batch,hout,wout] */
+int e4s_upsample_argmax_u8(const float* logits, int64_t pitch, int batch, int c, int hin, int win, int hout, int wout,
+                           const uint8_t* lut, uint8_t* labels, void* stream);
+
+/* FaceParser front-end: x NCHW [batch,3,hin,win] in [0,1] -> separable `factor*4`-tap bicubic down by `factor`
+ * (reflect pad), clamp(0,1) if do_clamp, (v-mean[c])/std[c]; output NHWC with c_pad channels.  tmp: [batch,3,hin/factor,win] floats */
+int e4s_bicubic_down_norm_f32(const float* x, int batch, int hin, int win, int factor, const float* taps,
+                              const float* mean, const float* std, float* tmp, float* y, int c_pad, int do_clamp, void* stream);
+
+/* labels u8 [batch,h,w] -> one-hot float [batch,k,h,w] (labelMap2OneHot, utils/torch_utils.py:207-213) */
+int e4s_labels_to_onehot_f32(const uint8_t* labels, int batch, int k, int h, int w, float* onehot, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E4S_B200_H */

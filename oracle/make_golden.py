@@ -122,7 +122,7 @@ def main():
         io, into = orc.generator_forward(sd, size, latent, mask, split_layer_idx=split, remaining_layer_idx=rl)
         report["generator/" + tag] = diff(img, io)
         report["generator/" + tag + "/inter"] = diff(inter, into)
-        save("generator_" + tag, labels=lab.numpy().astype(np.uint8), image=img.numpy(), inter=inter.numpy(),
+        save("generator_" + tag, labels=lab.numpy().astype(np.uint8), image=img.numpy(), inter=inter.numpy()[:, ::16],
              cfg=np.array([size, rl, split, K, 7]))
 
     # ---- FSEncoder_PSP on a 128^2 input ----------------------------------------------------------
@@ -161,7 +161,7 @@ def main():
     o, o16, o32 = seg(xi)
     q, q16, q32 = orc.bisenet_forward(sd, xi)
     report["bisenet/out"] = max(diff(o, q), diff(o16, q16), diff(o32, q32))
-    save("bisenet", x=xi.numpy(), out=o.numpy(), out16=o16.numpy()[:, :, ::4, ::4], out32=o32.numpy()[:, :, ::4, ::4])
+    save("bisenet", x=xi.numpy(), out=o.numpy()[:, :, ::2, ::2], out16=o16.numpy()[:, :, ::4, ::4], out32=o32.numpy()[:, :, ::4, ::4])
 
     down = ref_shims.bicubic_cls()(factor=2)
     down.cuda = ""
@@ -174,7 +174,8 @@ def main():
     top2 = torch.topk(logits, 2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1])[0].numpy()
     report["parser/labels_mismatch"] = float((orc.face_parse(sd, img01)[0] != lab12).sum())
-    save("parser", pre_sample=pre.numpy()[:, :, ::8, ::8], labels19=lab19, labels12=lab12, margin=margin.astype(np.float32))
+    save("parser", pre_sample=pre.numpy()[:, :, ::8, ::8], labels19=lab19, labels12=lab12, margin=margin.astype(np.float32),
+         logit_absmax=np.float32(logits.abs().max()))
     d4 = ref_shims.bicubic_cls()(factor=4)
     d4.cuda = ""
     report["parser/bicubic4"] = diff(d4(img01[:, :, :256, :256]), orc.bicubic_downsample(img01[:, :, :256, :256], 4))

@@ -79,7 +79,7 @@ def test_generator_small(golden):
         img, inter = orc.generator_forward(sd, size, latent, synth.onehot(lab, K), split_layer_idx=split,
                                            remaining_layer_idx=rl)
         close(img, g["image"], 1e-4)
-        close(inter, g["inter"], 1e-4)
+        close(inter[:, ::16], g["inter"], 1e-4)
 
 
 def test_encoder(golden):
@@ -98,7 +98,7 @@ def test_bisenet_and_parser(golden):
     g = golden("bisenet")
     sd = synth.fill_state_dict(bisenet_state_shapes(19), seed=10)
     o, o16, o32 = orc.bisenet_forward(sd, T(g["x"]))
-    close(o, g["out"], 1e-4)
+    close(o[:, :, ::2, ::2], g["out"], 1e-4)
     close(o16[:, :, ::4, ::4], g["out16"], 1e-4)
     close(o32[:, :, ::4, ::4], g["out32"], 1e-4)
     p = golden("parser")
@@ -106,7 +106,7 @@ def test_bisenet_and_parser(golden):
     close(orc.parser_preprocess(img01, 1024)[:, :, ::8, ::8], p["pre_sample"], 1e-6)
     lab = orc.face_parse(sd, img01)[0]
     bad = lab != p["labels12"]
-    assert bad.sum() == 0 or float(p["margin"][bad].max()) < 1e-5
+    assert bad.sum() == 0
 
 
 def test_seg_lut(golden):
