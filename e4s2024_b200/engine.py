@@ -19,6 +19,9 @@ from . import _lib as L
 _ENGINE = os.environ.get("E4S_CONV_ENGINE", "tc")
 
 
+PROFILE = None        # set to a list by bench.py to time every conv launch with CUDA events
+
+
 def set_conv_engine(name: str):
     global _ENGINE
     assert name in ("tc", "f32")
@@ -54,13 +57,18 @@ def tc_eligible(cin: int, cout: int) -> bool:
     return cin % 64 == 0 and cout % 16 == 0 and cout >= 32
 
 
+def tc_available() -> bool:
+    """True when the library was built with the tcgen05 engine."""
+    return int(L.lib().e4s_pack_weights_tc_bytes(1, 64, 32)) > 0
+
+
 def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, phases: int, want_tc: bool) -> PackedConv:
     cout_pad = pad_to(cout, 4)
     if cout_pad != cout:
         w_pkc = torch.nn.functional.pad(w_pkc, (0, cout_pad - cout))
     w_pkc = w_pkc.contiguous().float()
     pc = PackedConv(w_pkc, cin, cout, cout_pad, kh, kw, phases)
-    if want_tc and w_pkc.is_cuda and tc_eligible(cin, cout):
+    if want_tc and w_pkc.is_cuda and tc_eligible(cin, cout) and tc_available():
         pc.tc = L.pack_weights_tc(w_pkc, phases, pc.k, cout, cout_pad)
     return pc
 
@@ -196,7 +204,19 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     p.out, p.out_pitch, p.accumulate = out.ptr, out.pitch, int(accumulate)
     eng = engine or _ENGINE
     use_tc = eng == "tc" and pw.tc is not None
+    if PROFILE is None:
+        L.conv(p, pw.tc if use_tc else None)
+        return out
+    # bench.py's per-launch timing pass: CUDA events on the launching stream around this one kernel
+    m_exec = b * hout * wout
+    alg = 2.0 * (m_exec / 4 if up2 else m_exec) * pw.k * pw.cout      # conv_transpose counted at input resolution
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     L.conv(p, pw.tc if use_tc else None)
+    ev1.record()
+    PROFILE.append({"engine": "tc" if use_tc else "f32", "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
+                    "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1),
+                    "bytes": 4.0 * (b * hin * win * pw.cin + m_exec * pw.cout)})
     return out
 
 
