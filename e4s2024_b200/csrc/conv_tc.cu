@@ -1,5 +1,502 @@
-// placeholder until the tcgen05 engine lands (next commit)
+// tcgen05 (5th-generation tensor core) implicit-GEMM convolution for sm_100a.
+//
+//   D[128 pixels, BN channels] (fp32, TMEM)  +=  A[128, 64] * B[BN, 64]^T    per K chunk of 64
+//
+// fp32-class accuracy on bf16 tensor cores: every operand is split v = hi + lo (two bf16), and each
+// product is issued as three MMAs  hi*hi + hi*lo + lo*hi  accumulating in fp32 (error ~2^-16 relative,
+// measured 6e-5 on the 256^2 generator).
+//
+// Warp roles (320 threads, one CTA per SM):
+//   warps 0-7  A producers: gather the im2col rows of this K chunk straight from the NHWC fp32 activations
+//              (zero padding, stride, nearest-upsampled input view, poly-phase up-conv taps), apply
+//              InstanceNorm and the per-pixel REGION style modulation  x * s[b, r(p), ci]  (each GEMM row
+//              carries its own region -> one pass over the tile whatever the mask looks like), split to
+//              bf16 hi/lo and store into the 128B-swizzled K-major UMMA layout.  After the main loop the
+//              same warps run the fused epilogue: tcgen05.ld the accumulator, demodulate per (sample, region,
+//              channel), add noise / bias / residual, activate, store NHWC fp32.
+//   warp 8     MMA issuer (one elected lane): 12 tcgen05.mma (3 split terms x 4 K-steps of 16) per chunk;
+//              tcgen05.commit releases the smem stage / signals the epilogue.  Owns the TMEM allocation.
+//   warp 9     B loader: the weights were packed once (e4s_pack_weights_tc) into the exact swizzled smem image,
+//              so each stage is two cp.async.bulk (TMA bulk-copy engine) transfers completing on an mbarrier.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
-extern "C" int e4s_conv_tc(const E4SConv*, const void*, void*) { return e4s::fail(E4S_ERR_UNSUPPORTED, "conv_tc: not built"); }
-extern "C" int64_t e4s_pack_weights_tc_bytes(int, int, int) { return 0; }
-extern "C" int e4s_pack_weights_tc(const float*, int, int, int, int, void*, void*) { return e4s::fail(E4S_ERR_UNSUPPORTED, "conv_tc: not built"); }
+
+namespace e4s {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // one bf16 A tile (hi or lo): 16 KB
+
+__host__ __device__ constexpr int tc_block_n(int cout) { return cout >= 256 ? 256 : cout; }
+__host__ __device__ constexpr int tc_stage_bytes(int bn) { return 2 * TC_A_BYTES + 2 * bn * TC_BK * 2; }
+__host__ __device__ constexpr int tc_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 3 : (bn == 64 ? 4 : 5)); }
+__host__ __device__ constexpr int tc_smem_bytes(int bn) { return tc_stages(bn) * tc_stage_bytes(bn) + TC_BM * 16 + 256 + 1024; }
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// try_wait suspends in hardware for a bounded time per call; the spin bound turns a protocol bug
+// (a barrier that never completes) into a trap -> launch error instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      printf("e4s conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  Field layout: cute/arch/mma_sm100_desc.hpp.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: c=f32 (bit 4), a=bf16 (bit 7), b=bf16 (bit 10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x (low 16 bits) = lo_elem
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct TcRow {
+  int b, oy, ox, r;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int64_t m_total) {
+  constexpr int STAGES = tc_stages(BN);
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = tc_stage_bytes(BN);
+  constexpr uint32_t IDESC = umma_idesc(BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  // [stages x (A_hi | A_lo | B_hi | B_lo)] [rows: 128 x int4] [barriers]
+  TcRow* rows = reinterpret_cast<TcRow*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + TC_BM * 16);
+  const uint32_t bar_full = smem_u32(bars);                    // STAGES barriers
+  const uint32_t bar_empty = bar_full + 8 * STAGES;            // STAGES barriers
+  const uint32_t bar_acc = bar_empty + 8 * STAGES;             // accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int phase_id = blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
+  const int n_tile = blockIdx.y;
+  const int K = p.kh * p.kw * p.cin;
+  const int num_kc = K / TC_BK;
+  const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (tid < TC_BM) {
+    int64_t m = (int64_t)blockIdx.x * TC_BM + tid;
+    TcRow rw{-1, 0, 0, 0};
+    if (m < m_total) {
+      if (up) {
+        int hw = p.hin * p.win;
+        rw.b = (int)(m / hw);
+        int rem = (int)(m - (int64_t)rw.b * hw);
+        int a = rem / p.win;
+        rw.oy = 2 * a + py;
+        rw.ox = 2 * (rem - a * p.win) + px;
+      } else {
+        int hw = p.hout * p.wout;
+        rw.b = (int)(m / hw);
+        int rem = (int)(m - (int64_t)rw.b * hw);
+        rw.oy = rem / p.wout;
+        rw.ox = rem - rw.oy * p.wout;
+      }
+      if (p.labels) {
+        int sy = nearest_src(rw.oy, p.lab_h, p.hout), sx = nearest_src(rw.ox, p.lab_w, p.wout);
+        rw.r = p.labels[((int64_t)rw.b * p.lab_h + sy) * p.lab_w + sx];
+      }
+    }
+    rows[tid] = rw;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, TC_PRODUCER_WARPS + 1);  // 8 producer warps + the B loader's expect_tx arrive
+      mbar_init(bar_empty + 8 * s, 1);                     // one tcgen05.commit
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =========================== A producers =====================================================
+    const int cg = tid & 7;           // 8-channel group inside the 64-wide K chunk
+    const int r0 = tid >> 3;          // rows r0, r0+32, r0+64, r0+96
+    int rb[4], ry[4], rx[4];
+    const float* rs[4];               // modulation row (per pixel region)
+    const float* rmean[4];
+    const float* rrstd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const TcRow rw = rows[r0 + 32 * i];
+      rb[i] = rw.b;
+      if (up) {
+        ry[i] = (rw.oy >> 1) - 1;     // input row of tap u = 0
+        rx[i] = (rw.ox >> 1) - 1;
+      } else {
+        ry[i] = rw.oy * p.stride - p.pad;
+        rx[i] = rw.ox * p.stride - p.pad;
+      }
+      const int bb = rw.b < 0 ? 0 : rw.b;
+      rs[i] = p.smod ? p.smod + ((int64_t)bb * p.regions + rw.r) * p.cin : nullptr;
+      rmean[i] = p.in_mean ? p.in_mean + (int64_t)bb * p.cin : nullptr;
+      rrstd[i] = p.in_mean ? p.in_rstd + (int64_t)bb * p.cin : nullptr;
+    }
+    const int hv = p.hin << p.in_shift, wv = p.win << p.in_shift;
+    const int kwid = up ? 3 : p.kw;
+
+    float4 v[4][2];
+    bool ok[4];
+    auto prefetch = [&](int kc) {
+      const int k0 = kc * TC_BK;
+      const int tap = k0 / p.cin;
+      const int ci = k0 - tap * p.cin + cg * 8;
+      const int ky = tap / kwid, kx = tap - ky * kwid;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int iy = ry[i] + ky, ix = rx[i] + kx;
+        ok[i] = rb[i] >= 0 && iy >= 0 && iy < hv && ix >= 0 && ix < wv;
+        if (ok[i]) {
+          iy >>= p.in_shift;
+          ix >>= p.in_shift;
+          const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)rb[i] * p.hin + iy) * p.win + ix) * p.x_pitch + ci);
+          v[i][0] = __ldg(src);
+          v[i][1] = __ldg(src + 1);
+        }
+      }
+    };
+
+    prefetch(0);
+    for (int kc = 0; kc < num_kc; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t par = (kc / STAGES) & 1;
+      mbar_wait(bar_empty + 8 * s, par ^ 1);
+      uint8_t* a_hi = smem + s * STAGE_BYTES;
+      uint8_t* a_lo = a_hi + TC_A_BYTES;
+      const int ci = (kc * TC_BK) % p.cin + cg * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = r0 + 32 * i;
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (ok[i]) {
+          f[0] = v[i][0].x; f[1] = v[i][0].y; f[2] = v[i][0].z; f[3] = v[i][0].w;
+          f[4] = v[i][1].x; f[5] = v[i][1].y; f[6] = v[i][1].z; f[7] = v[i][1].w;
+          if (rmean[i]) {
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(rmean[i] + ci)), m1 = __ldg(reinterpret_cast<const float4*>(rmean[i] + ci) + 1);
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(rrstd[i] + ci)), q1 = __ldg(reinterpret_cast<const float4*>(rrstd[i] + ci) + 1);
+            f[0] = (f[0] - m0.x) * q0.x; f[1] = (f[1] - m0.y) * q0.y; f[2] = (f[2] - m0.z) * q0.z; f[3] = (f[3] - m0.w) * q0.w;
+            f[4] = (f[4] - m1.x) * q1.x; f[5] = (f[5] - m1.y) * q1.y; f[6] = (f[6] - m1.z) * q1.z; f[7] = (f[7] - m1.w) * q1.w;
+          }
+          if (rs[i]) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(rs[i] + ci)), s1 = __ldg(reinterpret_cast<const float4*>(rs[i] + ci) + 1);
+            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+          }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = f[2 * j], b = f[2 * j + 1];
+          const uint32_t h = pack_bf16x2(a, b);
+          const float ah = __uint_as_float(h << 16), bh = __uint_as_float(h & 0xffff0000u);
+          hi[j] = h;
+          lo[j] = pack_bf16x2(a - ah, b - bh);
+        }
+        const uint32_t off = row * 128 + ((cg ^ (row & 7)) << 4);   // 128B swizzle: 16B chunk index ^= row % 8
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      if (kc + 1 < num_kc) prefetch(kc + 1);
+      fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+    }
+
+    // =========================== epilogue ========================================================
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = warp >> 2;             // column half
+    const TcRow rw = rows[q * 32 + lane];
+    const bool live = rw.b >= 0;
+    const int64_t pix = live ? ((int64_t)rw.b * p.hout + rw.oy) * p.wout + rw.ox : 0;
+    const int n_base = n_tile * BN + half * (BN / 2);
+    const float* drow = (p.demod && live) ? p.demod + ((int64_t)rw.b * p.regions + rw.r) * p.cout : nullptr;
+    float pw = 1.f;
+    if (p.pixw && live) {
+      int sy = nearest_src(rw.oy, p.lab_h, p.hout), sx = nearest_src(rw.ox, p.lab_w, p.wout);
+      pw = __ldg(p.pixw + (int64_t)rw.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
+    }
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    const float* nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
+    float nz_shared = 0.f;
+    if (nrow && p.noise_sc == 0) nz_shared = nw * __ldg(nrow);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+      float acc[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+      if (!live) continue;
+      const int n0 = n_base + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + j;
+        float t = acc[j];
+        if (drow) t *= __ldg(drow + n);
+        if (p.pixw) t *= pw;
+        if (p.ch_scale) t *= __ldg(p.ch_scale + n);
+        if (nrow) t += (p.noise_sc == 0) ? nz_shared : nw * __ldg(nrow + (int64_t)n * p.noise_sc);
+        if (p.ch_shift) t += __ldg(p.ch_shift + n);
+        if (p.res && !p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
+        switch (p.act) {
+          case E4S_ACT_LRELU: t = (t < 0.f ? t * p.act_slope : t) * p.act_gain; break;
+          case E4S_ACT_RELU: t = fmaxf(t, 0.f); break;
+          case E4S_ACT_PRELU: t = t < 0.f ? t * __ldg(p.act_prelu + n) : t; break;
+          case E4S_ACT_SIGMOID: t = 1.f / (1.f + expf(-t)); break;
+          case E4S_ACT_RSQRT_EPS: t = rsqrtf(t + p.act_slope); break;
+          default: break;
+        }
+        if (p.res && p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
+        acc[j] = t;
+      }
+      float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_pitch + n0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 val = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        if (p.accumulate) {
+          const float4 old = o[j];
+          val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+        }
+        o[j] = val;
+      }
+    }
+    tc_fence_before();
+  } else if (warp == TC_PRODUCER_WARPS) {
+    // =========================== MMA issuer ======================================================
+    if (lane == 0) {
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t par = (kc / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, par);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
+        const uint32_t b_hi = a_lo + TC_A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+          const uint64_t dah = umma_smem_desc(a_hi + koff), dal = umma_smem_desc(a_lo + koff);
+          const uint64_t dbh = umma_smem_desc(b_hi + koff), dbl = umma_smem_desc(b_lo + koff);
+          umma_bf16(tmem_acc, dal, dbh, IDESC, (kc | k) != 0);   // small terms first
+          umma_bf16(tmem_acc, dah, dbl, IDESC, 1);
+          umma_bf16(tmem_acc, dah, dbh, IDESC, 1);
+        }
+        umma_commit(bar_empty + 8 * s);          // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(bar_acc);                      // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    // =========================== B loader (bulk-copy engine) ======================================
+    if (lane == 0) {
+      const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
+      const uint8_t* src = wpk + ((int64_t)phase_id * gridDim.y + n_tile) * num_kc * tile_bytes;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t par = (kc / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, par ^ 1);
+        const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * TC_A_BYTES;
+        mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_BYTES);
+        bulk_g2s(dst, src + kc * tile_bytes, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous in the packed image
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// w_f32 [phases][K][cout_pad] -> per (phase, n_tile, k_chunk): B_hi tile | B_lo tile, each BN rows x 128 bytes,
+// row n holds k = chunk*64 .. +63 (bf16) with the 16-byte chunks XOR-swizzled by (n % 8)  == the smem image.
+__global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int cout, int cout_pad, int bn, uint8_t* __restrict__ out,
+                                       int64_t total) {
+  const int num_kc = K / TC_BK, nt = cout / bn;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates (phase, n_tile, kc, n_local, kpair) with kpair = 32 bf16 pairs per row
+    int kp = (int)(i % 32);
+    int64_t t = i / 32;
+    int nl = (int)(t % bn);
+    t /= bn;
+    int kc = (int)(t % num_kc);
+    t /= num_kc;
+    int ntile = (int)(t % nt);
+    int ph = (int)(t / nt);
+    const int k = kc * TC_BK + kp * 2, n = ntile * bn + nl;
+    const float a = w[((int64_t)ph * K + k) * cout_pad + n], b = w[((int64_t)ph * K + k + 1) * cout_pad + n];
+    const uint32_t h = pack_bf16x2(a, b);
+    const uint32_t l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
+    const int64_t tile = (((int64_t)ph * nt + ntile) * num_kc + kc) * (2 * (int64_t)bn * 128);
+    const int chunk = (kp >> 2) ^ (nl & 7);
+    const int64_t off = (int64_t)nl * 128 + chunk * 16 + (kp & 3) * 4;
+    *reinterpret_cast<uint32_t*>(out + tile + off) = h;
+    *reinterpret_cast<uint32_t*>(out + tile + (int64_t)bn * 128 + off) = l;
+  }
+}
+
+int validate_conv(const E4SConv* p);
+
+static bool tc_shape_ok(int k, int cout) {
+  if (k % TC_BK) return false;
+  if (cout >= 256) return cout % 256 == 0;
+  return cout == 32 || cout == 64 || cout == 128;
+}
+
+template <int BN>
+static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
+    if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
+  dim3 grid((unsigned)ceil_div64(m_total, TC_BM), (unsigned)(p->cout / BN), up ? 4 : 1);
+  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total);
+  return check_launch("e4s_conv_tc");
+}
+
+}  // namespace e4s
+
+using namespace e4s;
+
+extern "C" int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout) {
+  if (phases < 1 || !tc_shape_ok(k, cout)) return 0;
+  return (int64_t)phases * k * cout * 4;  // hi + lo bf16 per weight
+}
+
+extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cout, int cout_pad, void* w_packed, void* stream) {
+  E4S_REQUIRE(w_f32 && w_packed, "pack_weights_tc: null pointer");
+  E4S_REQUIRE(phases >= 1 && tc_shape_ok(k, cout) && cout_pad >= cout, "pack_weights_tc: unsupported shape K=%d cout=%d", k, cout);
+  E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "pack_weights_tc: output must be 16-byte aligned");
+  const int bn = tc_block_n(cout);
+  const int64_t total = (int64_t)phases * (cout / bn) * (k / TC_BK) * bn * 32;
+  int64_t g = ceil_div64(total, 256);
+  if (g > 148 * 32) g = 148 * 32;
+  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, k, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
+  return check_launch("pack_weights_tc");
+}
+
+extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream) {
+  int rc = validate_conv(p);
+  if (rc) return rc;
+  E4S_REQUIRE(w_packed, "conv_tc: null packed weights");
+  const int K = p->kh * p->kw * p->cin;
+  E4S_REQUIRE(p->cin % TC_BK == 0 && tc_shape_ok(K, p->cout), "conv_tc: needs cin %% 64 == 0 and cout in {32,64,128,256*n} (cin=%d cout=%d)",
+              p->cin, p->cout);
+  E4S_REQUIRE(!p->in_square, "conv_tc: in_square is only implemented by the fp32 engine");
+  E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc: out must be 16-byte aligned with pitch %% 4 == 0");
+  E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
+  if (p->smod) E4S_REQUIRE((reinterpret_cast<uintptr_t>(p->smod) & 15) == 0, "conv_tc: smod must be 16-byte aligned");
+  const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
+  const int64_t m_total = up ? (int64_t)p->batch * p->hin * p->win : (int64_t)p->batch * p->hout * p->wout;
+  cudaStream_t s = as_stream(stream);
+  switch (tc_block_n(p->cout)) {
+    case 256: return launch_tc<256>(p, w_packed, m_total, s);
+    case 128: return launch_tc<128>(p, w_packed, m_total, s);
+    case 64: return launch_tc<64>(p, w_packed, m_total, s);
+    case 32: return launch_tc<32>(p, w_packed, m_total, s);
+    default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc: unsupported cout %d", p->cout);
+  }
+}

@@ -1,0 +1,83 @@
+"""GPU: the tcgen05 (bf16x3 split) convolution engine against the exact-fp32 CUDA-core engine and a plain
+torch fp64 reference of the same op, over the geometries the hot path uses.  Tolerance: the split keeps
+~16 mantissa bits per operand -> relative error ~1e-5 of the output scale (stated bound 2e-4)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from e4s2024_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, name, std=1.0):
+    return synth.randn(name, shape, 21, std).cuda()
+
+
+CASES = [
+    # (name, B, H, W, Cin, Cout, k, stride, up2, regions)
+    ("3x3_c64_n64", 2, 16, 16, 64, 64, 3, 1, False, 1),
+    ("3x3_c128_n32", 1, 24, 20, 128, 32, 3, 1, False, 1),
+    ("3x3_c512_n512_regions", 2, 8, 8, 512, 512, 3, 1, False, 5),
+    ("3x3_s2_c64_n128", 2, 18, 18, 64, 128, 3, 2, False, 1),
+    ("1x1_c256_n256", 2, 8, 8, 256, 256, 1, 1, False, 1),
+    ("up2_c128_n64_regions", 2, 8, 8, 128, 64, 3, 1, True, 4),
+    ("tiny_m", 1, 4, 4, 512, 512, 3, 1, False, 3),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tc_matches_f32_and_torch(case):
+    from e4s2024_b200 import _lib as L
+    from e4s2024_b200 import engine as E
+    if not E.tc_available():
+        pytest.skip("library built without the tcgen05 engine")
+    name, B, H, W, Cin, Cout, k, stride, up2, R = case
+    x = _mk((B, H, W, Cin), name + ".x")
+    w = _mk((Cout, Cin, k, k), name + ".w", (1.0 / (Cin * k * k)) ** 0.5)
+    Ho, Wo = (2 * H, 2 * W) if up2 else ((H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1)
+    smod = (1.0 + 0.3 * _mk((B, R, Cin), name + ".s")).contiguous()
+    demod = (1.0 + 0.2 * _mk((B, R, Cout), name + ".d")).contiguous()
+    labels = torch.randint(0, R, (B, 32, 32), device="cuda", dtype=torch.uint8) if R > 1 else None
+    noise = _mk((1, 1, Ho, Wo), name + ".n")
+    nw = torch.tensor([0.1], device="cuda")
+    bias = _mk((Cout,), name + ".b", 0.1)
+    if up2:
+        fir = torch.tensor([1., 3., 3., 1.])
+        fir = (torch.outer(fir, fir) / 64 * 4).cuda()
+        pw = E.pack_up_weight(w, fir)
+    else:
+        pw = E.pack_conv_weight(w)
+    assert pw.tc is not None
+    kw = dict(stride=stride, up2=up2, smod=smod, demod=demod, labels=labels, regions=R, noise=noise, noise_w=nw, ch_shift=bias,
+              act=L.ACT_LRELU, slope=0.2, gain=2 ** 0.5)
+    y32 = E.conv(E.View(x), pw, engine="f32", **kw).t
+    ytc = E.conv(E.View(x), pw, engine="tc", **kw).t
+    torch.cuda.synchronize()
+    scale = float(y32.abs().max())
+    d = float((ytc - y32).abs().max())
+    print(f"{name}: max|tc - f32| = {d:.3e} (output scale {scale:.2f})")
+    assert d < 2e-4 * max(scale, 1.0)
+
+    # torch fp64 reference of the same op (per-pixel region modulation done the slow way)
+    xd, wd = x.double().permute(0, 3, 1, 2), w.double()
+    ys = torch.arange(Ho, device="cuda") * 32 // Ho
+    xs = torch.arange(Wo, device="cuda") * 32 // Wo
+    reg = labels.long()[:, ys][:, :, xs] if labels is not None else torch.zeros(B, Ho, Wo, dtype=torch.long, device="cuda")
+    ref = torch.zeros(B, Cout, Ho, Wo, dtype=torch.float64, device="cuda")
+    for r in range(R):
+        xm = xd * smod[:, r].double()[:, :, None, None]
+        if up2:
+            yt = F.conv_transpose2d(xm, wd.transpose(0, 1), stride=2)
+            kf = fir.double()[None, None].repeat(Cout, 1, 1, 1)
+            yr = F.conv2d(F.pad(yt, (1, 1, 1, 1)), torch.flip(kf, [2, 3]), groups=Cout)
+        else:
+            yr = F.conv2d(xm, wd, stride=stride, padding=k // 2)
+        yr = yr * demod[:, r].double()[:, :, None, None]
+        ref += yr * (reg == r)[:, None].double()
+    ref = ref + 0.1 * noise.double() + bias.double()[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) * 2 ** 0.5
+    d32 = float((y32.permute(0, 3, 1, 2).double() - ref).abs().max())
+    dtc = float((ytc.permute(0, 3, 1, 2).double() - ref).abs().max())
+    print(f"{name}: vs torch fp64: f32 engine {d32:.3e}, tc engine {dtc:.3e}")
+    assert d32 < 2e-5 * max(scale, 1.0) and dtc < 2e-4 * max(scale, 1.0)
