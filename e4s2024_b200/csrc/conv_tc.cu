@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   const int phase_id = blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
   const int n_tile = blockIdx.y;
   const int K = p.kh * p.kw * p.cin;
-  const int num_kc = K / TC_BK;
+  const int num_kc = (K + TC_BK - 1) / TC_BK;   // K is zero-padded to a multiple of 64 in the packed weights
   const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
 
   // ---- one-time setup ---------------------------------------------------------------------------
@@ -238,14 +238,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     float4 v[4][2];
     bool ok[4];
     auto prefetch = [&](int kc) {
-      const int k0 = kc * TC_BK;
+      const int k0 = kc * TC_BK + cg * 8;            // this thread's 8 consecutive k (one tap: cin % 8 == 0)
       const int tap = k0 / p.cin;
-      const int ci = k0 - tap * p.cin + cg * 8;
+      const int ci = k0 - tap * p.cin;
       const int ky = tap / kwid, kx = tap - ky * kwid;
+      const bool tap_ok = k0 < K;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         int iy = ry[i] + ky, ix = rx[i] + kx;
-        ok[i] = rb[i] >= 0 && iy >= 0 && iy < hv && ix >= 0 && ix < wv;
+        ok[i] = tap_ok && rb[i] >= 0 && iy >= 0 && iy < hv && ix >= 0 && ix < wv;
         if (ok[i]) {
           iy >>= p.in_shift;
           ix >>= p.in_shift;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       mbar_wait(bar_empty + 8 * s, par ^ 1);
       uint8_t* a_hi = smem + s * STAGE_BYTES;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
-      const int ci = (kc * TC_BK) % p.cin + cg * 8;
+      const int ci = (kc * TC_BK + cg * 8) % p.cin;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = r0 + 32 * i;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
 // row n holds k = chunk*64 .. +63 (bf16) with the 16-byte chunks XOR-swizzled by (n % 8)  == the smem image.
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int cout, int cout_pad, int bn, uint8_t* __restrict__ out,
                                        int64_t total) {
-  const int num_kc = K / TC_BK, nt = cout / bn;
+  const int num_kc = (K + TC_BK - 1) / TC_BK, nt = cout / bn;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // i enumerates (phase, n_tile, kc, n_local, kpair) with kpair = 32 bf16 pairs per row
     int kp = (int)(i % 32);
@@ -424,7 +425,8 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int c
     int ntile = (int)(t % nt);
     int ph = (int)(t / nt);
     const int k = kc * TC_BK + kp * 2, n = ntile * bn + nl;
-    const float a = w[((int64_t)ph * K + k) * cout_pad + n], b = w[((int64_t)ph * K + k + 1) * cout_pad + n];
+    const float a = k < K ? w[((int64_t)ph * K + k) * cout_pad + n] : 0.f;
+    const float b = k + 1 < K ? w[((int64_t)ph * K + k + 1) * cout_pad + n] : 0.f;
     const uint32_t h = pack_bf16x2(a, b);
     const uint32_t l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
     const int64_t tile = (((int64_t)ph * nt + ntile) * num_kc + kc) * (2 * (int64_t)bn * 128);
@@ -438,7 +440,7 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int c
 int validate_conv(const E4SConv* p);
 
 static bool tc_shape_ok(int k, int cout) {
-  if (k % TC_BK) return false;
+  if (k < 8 || k % 8) return false;
   if (cout >= 256) return cout % 256 == 0;
   return cout == 32 || cout == 64 || cout == 128;
 }
@@ -463,7 +465,7 @@ using namespace e4s;
 
 extern "C" int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout) {
   if (phases < 1 || !tc_shape_ok(k, cout)) return 0;
-  return (int64_t)phases * k * cout * 4;  // hi + lo bf16 per weight
+  return (int64_t)phases * ((k + TC_BK - 1) / TC_BK * TC_BK) * cout * 4;  // hi + lo bf16 per (zero-padded) weight
 }
 
 extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cout, int cout_pad, void* w_packed, void* stream) {
@@ -471,7 +473,7 @@ extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int co
   E4S_REQUIRE(phases >= 1 && tc_shape_ok(k, cout) && cout_pad >= cout, "pack_weights_tc: unsupported shape K=%d cout=%d", k, cout);
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "pack_weights_tc: output must be 16-byte aligned");
   const int bn = tc_block_n(cout);
-  const int64_t total = (int64_t)phases * (cout / bn) * (k / TC_BK) * bn * 32;
+  const int64_t total = (int64_t)phases * (cout / bn) * ((k + TC_BK - 1) / TC_BK) * bn * 32;
   int64_t g = ceil_div64(total, 256);
   if (g > 148 * 32) g = 148 * 32;
   pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, k, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
@@ -483,8 +485,7 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
   if (rc) return rc;
   E4S_REQUIRE(w_packed, "conv_tc: null packed weights");
   const int K = p->kh * p->kw * p->cin;
-  E4S_REQUIRE(p->cin % TC_BK == 0 && tc_shape_ok(K, p->cout), "conv_tc: needs cin %% 64 == 0 and cout in {32,64,128,256*n} (cin=%d cout=%d)",
-              p->cin, p->cout);
+  E4S_REQUIRE(tc_shape_ok(K, p->cout), "conv_tc: needs cin %% 8 == 0 and cout in {32,64,128,256*n} (cin=%d cout=%d)", p->cin, p->cout);
   E4S_REQUIRE(!p->in_square, "conv_tc: in_square is only implemented by the fp32 engine");
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc: out must be 16-byte aligned with pitch %% 4 == 0");
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");

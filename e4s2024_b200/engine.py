@@ -54,7 +54,7 @@ class PackedConv:
 
 
 def tc_eligible(cin: int, cout: int) -> bool:
-    return cin % 64 == 0 and cout % 16 == 0 and cout >= 32
+    return cin % 8 == 0 and (cout in (32, 64, 128) or (cout >= 256 and cout % 256 == 0))
 
 
 def tc_available() -> bool:

@@ -108,7 +108,7 @@ int e4s_sizeof_conv(void);
 int e4s_conv_f32(const E4SConv* p, void* stream);
 
 /* tcgen05 (5th-gen tensor core) implicit GEMM with the 3-pass bf16 hi/lo split (fp32 accumulate in TMEM).
- * w points to the packed bf16 image produced by e4s_pack_weights_tc; cin % 64 == 0, cout % 16 == 0. */
+ * w points to the packed bf16 image produced by e4s_pack_weights_tc; cin % 8 == 0, cout in {32,64,128,256*n}. */
 int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream);
 /* bytes needed for the packed tensor-core weights of a [phases, K, cout] fp32 matrix */
 int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);

@@ -23,6 +23,10 @@ CASES = [
     ("1x1_c256_n256", 2, 8, 8, 256, 256, 1, 1, False, 1),
     ("up2_c128_n64_regions", 2, 8, 8, 128, 64, 3, 1, True, 4),
     ("tiny_m", 1, 4, 4, 512, 512, 3, 1, False, 3),
+    ("3x3_c32_n32", 1, 40, 40, 32, 32, 3, 1, False, 1),
+    ("3x3_c8_n64_rgb", 2, 20, 20, 8, 64, 3, 1, False, 1),
+    ("up2_c64_n32", 1, 12, 12, 64, 32, 3, 1, True, 1),
+    ("3x3_c16_n128_s2", 1, 14, 14, 16, 128, 3, 2, False, 2),
 ]
 
 
