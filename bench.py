@@ -89,24 +89,34 @@ def build_generator(device):
     return G.to(device).eval()
 
 
-def cpu_baseline(threads=None, faces=1, reps=1):
+def thread_candidates():
+    """torch/oneDNN does not scale to every hardware thread on big hosts (128 threads were 6x slower than 8 on the
+    first box), so the CPU arm tries a few thread counts and keeps the fastest; `cores` reports the one used."""
+    n = os.cpu_count() or 1
+    return sorted({n, min(n, 64), min(n, 32), min(n, 16)}, reverse=True)
+
+
+def cpu_baseline(faces=1):
     """The oracle (CPU restatement of the reference algorithm: K=12 grouped convs per masked layer) on the host cores."""
     from e4s2024_b200 import synth
     from e4s2024_b200.stylegan2.model import generator_state_shapes
     from oracle import e4s_oracle as orc
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     sd = synth.fill_state_dict(generator_state_shapes(SIZE, split_layer_idx=SPLIT, remaining_layer_idx=RL), seed=2)
     latent, mask = make_generator_inputs(faces)
-    best = None
+    best, best_t, tried = None, None, {}
     with torch.no_grad():
-        for _ in range(reps):
+        for t in thread_candidates():
+            torch.set_num_threads(t)
             t0 = time.perf_counter()
             orc.generator_forward(sd, SIZE, latent, mask, split_layer_idx=SPLIT, remaining_layer_idx=RL)
             dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return {"value": faces / best, "unit": "faces/s", "cores": threads, "kind": "port",
-            "sample": f"{faces} face(s), Generator 1024^2 K=12 rl=13, oracle/e4s_oracle.py, fp32, best of {reps}"}
+            tried[t] = round(dt, 2)
+            if best is None or dt < best:
+                best, best_t = dt, t
+            if dt > 45:                       # keep the whole bench within minutes
+                continue
+    return {"value": faces / best, "unit": "faces/s", "cores": best_t, "kind": "port",
+            "sample": f"{faces} face, Generator 1024^2 K=12 rl=13, oracle/e4s_oracle.py fp32; seconds per thread count {tried}"}
 
 
 def run_reference(args):
@@ -118,14 +128,21 @@ def run_reference(args):
     from e4s2024_b200 import synth
     from e4s2024_b200.stylegan2.model import generator_state_shapes
     from oracle import e4s_oracle as orc
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     sd = synth.fill_state_dict(generator_state_shapes(SIZE, split_layer_idx=SPLIT, remaining_layer_idx=RL), seed=2)
     latent, mask = make_generator_inputs(1)
     step = lambda: orc.generator_forward(sd, SIZE, latent, mask, split_layer_idx=SPLIT, remaining_layer_idx=RL)
+    cands = thread_candidates()
+    threads, best = cands[0], None
     with torch.no_grad():
-        for _ in range(args.warmup):
+        for i in range(max(args.warmup, 1)):          # warm-up steps double as the thread-count search
+            t = cands[i % len(cands)]
+            torch.set_num_threads(t)
+            t0 = time.perf_counter()
             step()
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, threads = dt, t
+        torch.set_num_threads(threads)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step()
