@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--impl", default="e4s_b200", choices=["e4s_b200", "reference"])
     ap.add_argument("--engine", default=None, choices=[None, "tc", "f32"], help="conv engine override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-layers", default=None, help="write per-conv-launch timings (JSON lines) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,11 +238,25 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
 
+    if os.environ.get("E4S_NCU"):          # one clean step for `ncu --profile-from-start off`
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+
     # ---- per-launch timing pass for the roofline of the dominant (convolution) kernel -----------------
     E.PROFILE = []
     step_resident()
     torch.cuda.synchronize()
     prof, E.PROFILE = E.PROFILE, None
+    if args.dump_layers and rank == 0:
+        with open(args.dump_layers, "w") as f:
+            for r in prof:
+                ms_l = r["ev"][0].elapsed_time(r["ev"][1])
+                f.write(json.dumps({"engine": r["engine"], "m": r["m"], "k": r["k"], "n": r["n"], "up2": r["up2"], "ms": round(ms_l, 4),
+                                    "exec_tflops": round(r["exec_flops"] / ms_l / 1e9, 2),
+                                    "io_gbs": round(r["bytes"] / ms_l / 1e6, 1)}) + "\n")
     by = {}
     for r in prof:
         d = by.setdefault(r["engine"], {"ms": 0.0, "alg": 0.0, "exec": 0.0, "n": 0})

@@ -1,0 +1,389 @@
+// tcgen05 "halo" convolution: 3x3 stride-1 convolutions (and the poly-phase up-convolution) whose A-operand
+// transform is uniform over a tile -- the un-masked StyleGAN2 layers (one style per sample: 512^2 / 1024^2, the
+// HBM-heavy layers) and the encoder's stride-1 convs (InstanceNorm per sample/channel).
+//
+// The gather engine (conv_tc.cu) rebuilds an im2col A tile per tap: 9x (36x for up-convs) redundant loads,
+// normalise/modulate/split work and shared-memory stores -- it is LSU/latency bound on the small-N layers
+// (profiles/r1_ncu_conv_tc_v1_per_layer.csv: 3-8 % tensor pipe at 512^2/1024^2).  Here the producers convert the
+// (16+2) x (8+2) pixel input HALO of a 16x8 output tile ONCE per 64-channel group into bf16 hi/lo planes stored
+// pixel-major with the 128-byte swizzle on absolute shared-memory addresses, and the 9 taps are 9 UMMA descriptors
+// whose start address is shifted by (ky*10 + kx) pixel rows with SBO = one halo row (1280 B).  tests/micro/
+// umma_shift.cu established on hardware that the tensor core applies the swizzle to absolute address bits, so
+// such row-shifted windows (start not 1024-aligned, base_offset 0, arbitrary SBO) read back exactly.
+// The four phases of an up-convolution reuse the same halo with four accumulators in TMEM.
+//
+// Persistent CTAs (one per SM), 448 threads:
+//   warps 0-7   halo producers: coalesced NHWC fp32 loads -> InstanceNorm / style modulation -> bf16 hi/lo split ->
+//               swizzled st.shared; one-job-ahead register prefetch
+//   warps 8-11  epilogue: tcgen05.ld -> demod / noise / bias / residual / activation -> NHWC fp32 stores
+//   warp 12     MMA issuer + TMEM owner (accumulator sets double-buffered when 2*P*BN <= 512 columns)
+//   warp 13     weight loader: cp.async.bulk of the pre-swizzled bf16 hi|lo tiles into a ring of stages
+#include "tc_ptx.cuh"
+
+namespace e4s {
+
+constexpr int HL_TH = 16, HL_TW = 8;
+constexpr int HL_HP = HL_TW + 2;                  // halo row pitch (pixels)
+constexpr int HL_HPIX = (HL_TH + 2) * HL_HP;      // 180 halo pixels
+constexpr int HL_PLANE = 23 * 1024;               // one bf16 plane (hi or lo): 180 * 128 B rounded up to 1 KB
+constexpr int HL_HALO_STAGES = 2;
+constexpr int HL_THREADS = 14 * 32;
+constexpr int HL_EPI_WARP0 = 8, HL_MMA_WARP = 12, HL_LOAD_WARP = 13;
+constexpr int HL_ITEMS = (HL_HPIX + 31) / 32;     // 6 (pixel, 8-channel) items per producer thread
+
+__host__ __device__ constexpr int hl_b_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 4 : 6); }
+__host__ __device__ constexpr int hl_smem_bytes(int bn) {
+  return HL_HALO_STAGES * 2 * HL_PLANE + hl_b_stages(bn) * 2 * bn * 128 + 512 + 1024;
+}
+
+__device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct HlJob {
+  int b, y0, x0, nt;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
+                    const int total_jobs) {
+  constexpr int BST = hl_b_stages(BN);
+  constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of a packed 64-wide K chunk
+  constexpr uint32_t IDESC = umma_idesc(BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  // [halo stage 0: hi | lo][halo stage 1: hi | lo][B ring: BST x (hi | lo)][barriers]
+  constexpr int HALO_BYTES = 2 * HL_PLANE;
+  constexpr int B_OFF = HL_HALO_STAGES * HALO_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * 2 * B_BYTES);
+  const uint32_t bar_hfull = smem_u32(bars);                 // 2
+  const uint32_t bar_hempty = bar_hfull + 16;                // 2
+  const uint32_t bar_bfull = bar_hempty + 16;                // BST
+  const uint32_t bar_bempty = bar_bfull + 8 * BST;           // BST
+  const uint32_t bar_afull = bar_bempty + 8 * BST;           // 2
+  const uint32_t bar_aempty = bar_afull + 16;                // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * BST);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
+  const int P = up ? 4 : 1;
+  const int cin_eff = p.cin < 64 ? p.cin : 64;               // channels per halo row actually used
+  const int G = p.cin < 64 ? 1 : p.cin / 64;                 // 64-channel groups
+  const int ksteps = cin_eff / 16;
+  const int tpc = 64 / cin_eff;                              // taps per packed 64-wide K chunk (1, or 2 when cin == 32)
+  const int CPG = (9 + tpc - 1) / tpc;                       // packed chunks per (phase, group)
+  const int num_kc = (9 * p.cin + 63) / 64;
+  const int nsets = (2 * P * BN <= 512) ? 2 : 1;
+  const int my_jobs = (total_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  auto decode = [&](int it) {
+    int j = (int)blockIdx.x + it * (int)gridDim.x;
+    HlJob r;
+    r.nt = j % n_tiles;
+    j /= n_tiles;
+    r.x0 = (j % tiles_x) * HL_TW;
+    j /= tiles_x;
+    r.y0 = (j % tiles_y) * HL_TH;
+    r.b = j / tiles_y;
+    return r;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_hfull + 8 * s, TC_PRODUCER_WARPS);
+      mbar_init(bar_hempty + 8 * s, 1);
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 4);
+    }
+    for (int s = 0; s < BST; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(nsets * P * BN)) tmem_cols <<= 1;
+  if (warp == HL_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =========================== halo producers ===================================================
+    const int cg = tid & 7;
+    const int px0 = tid >> 3;                                // halo pixels px0, px0+32, ...
+    const bool cg_live = cg * 8 < cin_eff;
+    const int total_hg = my_jobs * G;                        // halo fills this CTA performs
+
+    float4 v[HL_ITEMS][2];
+    uint32_t okm = 0;
+    float4 sc[2], mn[2], rs[2];                              // per-(sample, channel) modulation / InstanceNorm of this fill
+    auto prefetch = [&](int hg) {
+      okm = 0;
+      if (hg >= total_hg || !cg_live) return;
+      const int it = hg / G, g = hg - it * G;
+      const HlJob jb = decode(it);
+      const int ch = g * 64 + cg * 8;
+      if (p.smod) {
+        const float4* sp = reinterpret_cast<const float4*>(p.smod + (int64_t)jb.b * p.regions * p.cin + ch);
+        sc[0] = __ldg(sp);
+        sc[1] = __ldg(sp + 1);
+      }
+      if (p.in_mean) {
+        const float4* mp = reinterpret_cast<const float4*>(p.in_mean + (int64_t)jb.b * p.cin + ch);
+        const float4* qp = reinterpret_cast<const float4*>(p.in_rstd + (int64_t)jb.b * p.cin + ch);
+        mn[0] = __ldg(mp); mn[1] = __ldg(mp + 1);
+        rs[0] = __ldg(qp); rs[1] = __ldg(qp + 1);
+      }
+#pragma unroll
+      for (int i = 0; i < HL_ITEMS; ++i) {
+        const int px = px0 + 32 * i;
+        const int hy = px / HL_HP, hx = px - hy * HL_HP;
+        const int iy = jb.y0 - 1 + hy, ix = jb.x0 - 1 + hx;
+        if (px < HL_HPIX && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
+          okm |= 1u << i;
+          const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)jb.b * p.hin + iy) * p.win + ix) * p.x_pitch + ch);
+          v[i][0] = __ldg(src);
+          v[i][1] = __ldg(src + 1);
+        }
+      }
+    };
+
+    prefetch(0);
+    for (int hg = 0; hg < total_hg; ++hg) {
+      const int hs = hg & 1;
+      mbar_wait(bar_hempty + 8 * hs, ((hg >> 1) & 1) ^ 1);
+      uint8_t* h_hi = smem + hs * HALO_BYTES;
+      uint8_t* h_lo = h_hi + HL_PLANE;
+      if (cg_live) {
+#pragma unroll
+        for (int i = 0; i < HL_ITEMS; ++i) {
+          const int px = px0 + 32 * i;
+          if (px >= HL_HPIX) continue;
+          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (okm & (1u << i)) {
+            f[0] = v[i][0].x; f[1] = v[i][0].y; f[2] = v[i][0].z; f[3] = v[i][0].w;
+            f[4] = v[i][1].x; f[5] = v[i][1].y; f[6] = v[i][1].z; f[7] = v[i][1].w;
+            if (p.in_mean) {
+              f[0] = (f[0] - mn[0].x) * rs[0].x; f[1] = (f[1] - mn[0].y) * rs[0].y; f[2] = (f[2] - mn[0].z) * rs[0].z; f[3] = (f[3] - mn[0].w) * rs[0].w;
+              f[4] = (f[4] - mn[1].x) * rs[1].x; f[5] = (f[5] - mn[1].y) * rs[1].y; f[6] = (f[6] - mn[1].z) * rs[1].z; f[7] = (f[7] - mn[1].w) * rs[1].w;
+            }
+            if (p.smod) {
+              f[0] *= sc[0].x; f[1] *= sc[0].y; f[2] *= sc[0].z; f[3] *= sc[0].w;
+              f[4] *= sc[1].x; f[5] *= sc[1].y; f[6] *= sc[1].z; f[7] *= sc[1].w;
+            }
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = f[2 * j], b = f[2 * j + 1];
+            const uint32_t h = pack_bf16x2(a, b);
+            hi[j] = h;
+            lo[j] = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
+          }
+          const uint32_t off = px * 128 + ((cg ^ (px & 7)) << 4);       // swizzle on the absolute 128B-row index
+          *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      prefetch(hg + 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
+    }
+  } else if (warp < HL_MMA_WARP) {
+    // =========================== epilogue warpgroup ===============================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                           // GEMM row = ty*8 + tx
+    const int ty = row >> 3, tx = row & 7;
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    for (int it = 0; it < my_jobs; ++it) {
+      const HlJob jb = decode(it);
+      const int set = nsets == 2 ? (it & 1) : 0;
+      const int use = nsets == 2 ? (it >> 1) : it;
+      mbar_wait(bar_afull + 8 * set, use & 1);
+      tc_fence_after();
+      const float* drow = p.demod ? p.demod + (int64_t)jb.b * p.regions * p.cout : nullptr;
+      for (int ph = 0; ph < P; ++ph) {
+        const int oy = up ? 2 * (jb.y0 + ty) + (ph >> 1) : jb.y0 + ty;
+        const int ox = up ? 2 * (jb.x0 + tx) + (ph & 1) : jb.x0 + tx;
+        const int64_t pix = ((int64_t)jb.b * p.hout + oy) * p.wout + ox;
+        float pw = 1.f;
+        if (p.pixw) {
+          const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
+          pw = __ldg(p.pixw + (int64_t)jb.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
+        }
+        const float* nrow = p.noise ? p.noise + (int64_t)jb.b * p.noise_sb + (int64_t)oy * p.wout + ox : nullptr;
+        float nz_shared = 0.f;
+        if (nrow && p.noise_sc == 0) nz_shared = nw * __ldg(nrow);
+        const uint32_t tacc = tmem_base + (uint32_t)((set * P + ph) * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float acc[16];
+          tmem_ld16(tacc + (uint32_t)c0, acc);
+          const int n0 = jb.nt * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            float t = acc[j];
+            if (drow) t *= __ldg(drow + n);
+            if (p.pixw) t *= pw;
+            if (p.ch_scale) t *= __ldg(p.ch_scale + n);
+            if (nrow) t += (p.noise_sc == 0) ? nz_shared : nw * __ldg(nrow + (int64_t)n * p.noise_sc);
+            if (p.ch_shift) t += __ldg(p.ch_shift + n);
+            if (p.res && !p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
+            switch (p.act) {
+              case E4S_ACT_LRELU: t = (t < 0.f ? t * p.act_slope : t) * p.act_gain; break;
+              case E4S_ACT_RELU: t = fmaxf(t, 0.f); break;
+              case E4S_ACT_PRELU: t = t < 0.f ? t * __ldg(p.act_prelu + n) : t; break;
+              case E4S_ACT_SIGMOID: t = 1.f / (1.f + expf(-t)); break;
+              case E4S_ACT_RSQRT_EPS: t = rsqrtf(t + p.act_slope); break;
+              default: break;
+            }
+            if (p.res && p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
+            acc[j] = t;
+          }
+          float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_pitch + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 val = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            if (p.accumulate) {
+              const float4 old = o[j];
+              val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+            }
+            o[j] = val;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_aempty + 8 * set);
+    }
+  } else if (warp == HL_MMA_WARP) {
+    // =========================== MMA issuer ======================================================
+    if (lane == 0) {
+      int hg = 0, bc = 0;                                    // running halo-fill and weight-chunk counters
+      for (int it = 0; it < my_jobs; ++it) {
+        const int set = nsets == 2 ? (it & 1) : 0;
+        const int use = nsets == 2 ? (it >> 1) : it;
+        mbar_wait(bar_aempty + 8 * set, (use & 1) ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < G; ++g, ++hg) {
+          const int hs = hg & 1;
+          mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
+          tc_fence_after();
+          const uint32_t h_hi = smem_base + hs * HALO_BYTES, h_lo = h_hi + HL_PLANE;
+          for (int ph = 0; ph < P; ++ph) {
+            const uint32_t tacc = tmem_base + (uint32_t)((set * P + ph) * BN);
+            for (int c = 0; c < CPG; ++c, ++bc) {
+              const int bs = bc % BST;
+              mbar_wait(bar_bfull + 8 * bs, (bc / BST) & 1);
+              tc_fence_after();
+              const uint32_t b_hi = smem_base + B_OFF + bs * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
+              for (int tt = 0; tt < tpc; ++tt) {
+                const int tap = c * tpc + tt;
+                if (tap >= 9) break;
+                const uint32_t aoff = (uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u;
+                const uint32_t boff = (uint32_t)(tt * cin_eff * 2);
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t dah = umma_smem_desc_sbo(h_hi + aoff + k * 32, HL_HP * 128);
+                  const uint64_t dal = umma_smem_desc_sbo(h_lo + aoff + k * 32, HL_HP * 128);
+                  const uint64_t dbh = umma_smem_desc(b_hi + boff + k * 32), dbl = umma_smem_desc(b_lo + boff + k * 32);
+                  umma_bf16(tacc, dal, dbh, IDESC, (g | tap | k) != 0);
+                  umma_bf16(tacc, dah, dbl, IDESC, 1);
+                  umma_bf16(tacc, dah, dbh, IDESC, 1);
+                }
+              }
+              umma_commit(bar_bempty + 8 * bs);
+            }
+          }
+          umma_commit(bar_hempty + 8 * hs);                  // every tap of every phase has read this halo
+        }
+        umma_commit(bar_afull + 8 * set);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight loader ====================================================
+    if (lane == 0) {
+      const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
+      int bc = 0;
+      for (int it = 0; it < my_jobs; ++it) {
+        const HlJob jb = decode(it);
+        for (int g = 0; g < G; ++g)
+          for (int ph = 0; ph < P; ++ph) {
+            const uint8_t* src = wpk + ((int64_t)ph * n_tiles + jb.nt) * num_kc * tile_bytes;
+            for (int c = 0; c < CPG; ++c, ++bc) {
+              const int bs = bc % BST;
+              const int kc = tpc == 1 ? c * G + g : c;       // packed chunk = k / 64 with k = tap*cin + ci
+              mbar_wait(bar_bempty + 8 * bs, ((bc / BST) & 1) ^ 1);
+              mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * B_BYTES);
+              bulk_g2s(smem_base + B_OFF + bs * 2 * B_BYTES, src + kc * tile_bytes, 2 * B_BYTES, bar_bfull + 8 * bs);
+            }
+          }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == HL_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+static int g_halo_sm_count = 0;
+
+// geometry the halo kernel takes (everything else stays on the gather kernel)
+bool tc_halo_eligible(const E4SConv* p) {
+  const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
+  if (!up && !(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && p->in_shift == 0)) return false;
+  if (p->labels) return false;                               // per-pixel regions need the per-row gather path
+  if (p->hin % HL_TH || p->win % HL_TW) return false;
+  if (!(p->cin == 32 || p->cin % 64 == 0)) return false;
+  const int bn = tc_block_n(p->cout);
+  if ((up ? 4 : 1) * bn > 512) return false;
+  return true;
+}
+
+template <int BN>
+static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl_smem_bytes(BN));
+    if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  if (g_halo_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_halo_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_halo_sm_count <= 0) g_halo_sm_count = 148;
+  }
+  const int tiles_x = p->win / HL_TW, tiles_y = p->hin / HL_TH, n_tiles = p->cout / BN;
+  const int64_t total = (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
+  E4S_REQUIRE(total < 0x7fffffff, "conv_tc(halo): too many tiles");
+  const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
+  conv_tc_halo_kernel<BN><<<grid, HL_THREADS, hl_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
+                                                                     (int)total);
+  return check_launch("e4s_conv_tc(halo)");
+}
+
+int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
+  switch (tc_block_n(p->cout)) {
+    case 256: return launch_halo<256>(p, wpk, s);
+    case 128: return launch_halo<128>(p, wpk, s);
+    case 64: return launch_halo<64>(p, wpk, s);
+    case 32: return launch_halo<32>(p, wpk, s);
+    default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc(halo): unsupported cout %d", p->cout);
+  }
+}
+
+}  // namespace e4s

@@ -27,6 +27,14 @@ CASES = [
     ("3x3_c8_n64_rgb", 2, 20, 20, 8, 64, 3, 1, False, 1),
     ("up2_c64_n32", 1, 12, 12, 64, 32, 3, 1, True, 1),
     ("3x3_c16_n128_s2", 1, 14, 14, 16, 128, 3, 2, False, 2),
+    # geometries taken by the halo kernel (H % 16 == 0, W % 8 == 0, one style per sample)
+    ("halo_c32_n32", 1, 32, 48, 32, 32, 3, 1, False, 1),
+    ("halo_c64_n64", 3, 32, 24, 64, 64, 3, 1, False, 1),
+    ("halo_c128_n256", 1, 32, 16, 128, 256, 3, 1, False, 1),
+    ("halo_c512_n512", 1, 16, 16, 512, 512, 3, 1, False, 1),
+    ("halo_up2_c64_n32", 2, 16, 16, 64, 32, 3, 1, True, 1),
+    ("halo_up2_c128_n64", 2, 16, 8, 128, 64, 3, 1, True, 1),
+    ("halo_up2_c32_n32", 1, 32, 16, 32, 32, 3, 1, True, 1),
 ]
 
 

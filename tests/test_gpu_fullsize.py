@@ -99,3 +99,50 @@ def test_parser_batch_is_batch_invariant():
     lab = parser.parse_batch(img01)
     assert lab.shape == (3, 512, 512) and lab.dtype == torch.uint8 and int(lab.max()) < 12
     assert torch.equal(parser.parse_batch(img01[1:2])[0], lab[1])
+
+
+def test_net3_1024_vs_oracle():
+    """BASELINE config 3 shape (encoder -> regional styles -> synthesis) at 1024^2, B=2 on the GPU vs the oracle."""
+    from oracle.ref_shims import net3_opts
+    from e4s2024_b200.networks import Net3
+    net = Net3(net3_opts(out_size=1024, remaining_layer_idx=13))
+    sd = synth.synth_module_weights(net, seed=9)
+    net = net.cuda()
+    la = synth.randn("net3.latent_avg", (18, 512), 9, 0.1)
+    net.latent_avg = la.cuda()
+    img = synth.smooth_image("net3full.img", 2, 1024, 13)
+    mask = synth.onehot(synth.blocky_labels(2, 12, 512, cells=32, seed=13), 12)
+    out, inter = net(img.cuda(), mask.cuda(), randomize_noise=False)
+    assert out.shape == (2, 3, 1024, 1024) and inter.shape == (2, 512, 16, 16)
+    sdc = {k: v.cpu() for k, v in sd.items()}
+    ro, _, rcodes, rvec = orc.net3_forward(sdc, img[:1], mask[:1], la, out_size=1024, remaining_layer_idx=13)
+    vec, _ = net.get_style_vectors(img.cuda(), mask.cuda())
+    dv = float((vec[:1].cpu() - rvec).abs().max())
+    di = float((out[:1].cpu() - ro).abs().max())
+    print(f"Net3 1024^2: style vectors max|diff| {dv:.3e} (scale {float(rvec.abs().max()):.2f}), image {di:.3e} (range {float(ro.abs().max()):.2f})")
+    assert dv < 1e-3 and di < 1e-3
+    solo, _ = net(img[1:].cuda(), mask[1:].cuda(), randomize_noise=False)
+    assert torch.equal(solo[0], out[1])
+
+
+def test_bisenet_512_argmax_vs_oracle():
+    """BASELINE config 4 shape at B=4: argmax label maps vs the oracle; mismatches only where the oracle's own
+    top-2 margin is within fp32 reassociation noise of a tie."""
+    from e4s2024_b200.face_parsing.model import BiSeNet
+    seg = BiSeNet(19)
+    sd = synth.synth_module_weights(seg, seed=10)
+    seg = seg.cuda().eval()
+    x = synth.randn("bise512.x", (4, 3, 512, 512), 14)
+    o, o16, o32 = seg(x.cuda())
+    ref = orc.bisenet_forward({k: v.cpu() for k, v in sd.items()}, x)[0]
+    scale = float(ref.abs().max())
+    d = float((o.cpu() - ref).abs().max())
+    lab, rlab = o.argmax(1).cpu(), ref.argmax(1)
+    bad = lab != rlab
+    top2 = torch.topk(ref, 2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    worst = float(margin[bad].max()) if bad.any() else 0.0
+    print(f"BiSeNet 512^2 B=4: logits max|diff| {d:.3e} (scale {scale:.1f}); label mismatches {int(bad.sum())} of {bad.numel()}, "
+          f"largest oracle margin at a mismatch {worst:.3e}")
+    assert d < 3e-5 * scale
+    assert int(bad.sum()) <= 16 and worst < 2e-5 * scale
