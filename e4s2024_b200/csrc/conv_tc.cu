@@ -205,47 +205,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       int sy = nearest_src(rw.oy, p.lab_h, p.hout), sx = nearest_src(rw.ox, p.lab_w, p.wout);
       pw = __ldg(p.pixw + (int64_t)rw.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
     }
-    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
-    const float* nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
-    float nz_shared = 0.f;
-    if (nrow && p.noise_sc == 0) nz_shared = nw * __ldg(nrow);
+    TcEpiRow er;
+    er.pix = pix;
+    er.drow = drow;
+    er.pw = pw;
+    er.nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    er.nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
+    er.nz = (er.nrow && p.noise_sc == 0) ? er.nw * __ldg(er.nrow) : 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN / 2; c0 += 16) {
       float acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
-      if (!live) continue;
-      const int n0 = n_base + c0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + j;
-        float t = acc[j];
-        if (drow) t *= __ldg(drow + n);
-        if (p.pixw) t *= pw;
-        if (p.ch_scale) t *= __ldg(p.ch_scale + n);
-        if (nrow) t += (p.noise_sc == 0) ? nz_shared : nw * __ldg(nrow + (int64_t)n * p.noise_sc);
-        if (p.ch_shift) t += __ldg(p.ch_shift + n);
-        if (p.res && !p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
-        switch (p.act) {
-          case E4S_ACT_LRELU: t = (t < 0.f ? t * p.act_slope : t) * p.act_gain; break;
-          case E4S_ACT_RELU: t = fmaxf(t, 0.f); break;
-          case E4S_ACT_PRELU: t = t < 0.f ? t * __ldg(p.act_prelu + n) : t; break;
-          case E4S_ACT_SIGMOID: t = 1.f / (1.f + expf(-t)); break;
-          case E4S_ACT_RSQRT_EPS: t = rsqrtf(t + p.act_slope); break;
-          default: break;
-        }
-        if (p.res && p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
-        acc[j] = t;
-      }
-      float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_pitch + n0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 val = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        if (p.accumulate) {
-          const float4 old = o[j];
-          val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-        }
-        o[j] = val;
-      }
+      if (live) tc_epilogue16(p, acc, n_base + c0, er);
     }
     tc_fence_before();
   } else if (warp == TC_PRODUCER_WARPS) {
@@ -324,356 +295,11 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int c
   }
 }
 
-// ===================================================================================================
-// v2: persistent, cross-tile pipelined kernel.
-//
-// v1 (above) starts one CTA per tile: its prologue (barrier init, TMEM alloc), the first exposed load
-// latency and the epilogue are all serialised per tile, and the producers prefetch only one K chunk ahead, so
-// the tensor pipe sat at 3-35 % (profiles/r1_ncu_conv_tc_v1_per_layer.csv).  v2 runs one CTA per SM for the
-// whole layer:  tiles are walked round-robin; the A producers stream K chunks CONTINUOUSLY across tile
-// boundaries with a two-deep register prefetch (each buffer carries the row bookkeeping of its own tile);
-// the accumulator is double-buffered in TMEM (2 x BN columns) and a dedicated warpgroup runs the epilogue of
-// tile i while the MMA warp is already accumulating tile i+1.
-//
-//   warps 0-7   A producers (gather / InstanceNorm / region modulation / bf16 hi-lo split / swizzled st.shared)
-//   warps 8-11  epilogue (tcgen05.ld -> demod, noise, bias, residual, activation -> NHWC store)
-//   warp  12    MMA issuer + TMEM owner          warp 13   weight loader (cp.async.bulk)
-// ===================================================================================================
-constexpr int TC2_THREADS = 14 * 32;
-constexpr int TC2_EPI_WARP0 = 8, TC2_MMA_WARP = 12, TC2_LOAD_WARP = 13;
-
-__host__ __device__ constexpr int tc2_smem_bytes(int bn) { return tc_stages(bn) * tc_stage_bytes(bn) + 256 + 1024; }
-
-struct TcTile {
-  int mt, nt, ph;
-};
-__device__ __forceinline__ TcTile tc_decode_tile(int t, int m_tiles, int n_tiles) {
-  TcTile r;
-  r.nt = t % n_tiles;
-  int q = t / n_tiles;
-  r.mt = q % m_tiles;
-  r.ph = q / m_tiles;
-  return r;
-}
-// output pixel of GEMM row `m` (tile-global row index) -> (b, oy, ox); b = -1 past the end
-__device__ __forceinline__ void tc_row_pixel(const E4SConv& p, int64_t m, int64_t m_total, int ph, int& b, int& oy, int& ox) {
-  b = -1;
-  oy = ox = 0;
-  if (m >= m_total) return;
-  if (p.mode == E4S_CONV_UP2_POLYPHASE) {
-    const int hw = p.hin * p.win;
-    b = (int)(m / hw);
-    const int rem = (int)(m - (int64_t)b * hw);
-    const int a = rem / p.win;
-    oy = 2 * a + (ph >> 1);
-    ox = 2 * (rem - a * p.win) + (ph & 1);
-  } else {
-    const int hw = p.hout * p.wout;
-    b = (int)(m / hw);
-    const int rem = (int)(m - (int64_t)b * hw);
-    oy = rem / p.wout;
-    ox = rem - oy * p.wout;
-  }
-}
-__device__ __forceinline__ int tc_row_region(const E4SConv& p, int b, int oy, int ox) {
-  if (!p.labels || b < 0) return 0;
-  const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
-  return p.labels[((int64_t)b * p.lab_h + sy) * p.lab_w + sx];
-}
-
-struct TcRows {       // bookkeeping of the 4 GEMM rows one producer thread gathers, for one tile
-  int tile;           // tile index these rows belong to (-1 = none)
-  int b[4], y[4], x[4], r[4];
-};
-
-template <int BN>
-__global__ void __launch_bounds__(TC2_THREADS, 1)
-conv_tc_persist_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int64_t m_total, const int m_tiles, const int n_tiles,
-                       const int total_tiles) {
-  constexpr int STAGES = tc_stages(BN);
-  constexpr int B_BYTES = BN * TC_BK * 2;
-  constexpr int STAGE_BYTES = tc_stage_bytes(BN);
-  constexpr uint32_t IDESC = umma_idesc(BN);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_acc_full = bar_empty + 8 * STAGES;    // 2 barriers
-  const uint32_t bar_acc_empty = bar_acc_full + 16;        // 2 barriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K = p.kh * p.kw * p.cin;
-  const int num_kc = (K + TC_BK - 1) / TC_BK;
-  const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
-  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +grid, ...
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, TC_PRODUCER_WARPS + 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, 4);     // the four epilogue warps
-    }
-    fence_barrier_init();
-    fence_proxy_async_smem();
-  }
-  if (warp == TC2_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // =========================== A producers =====================================================
-    const int cg = tid & 7;
-    const int r0 = tid >> 3;
-    const int hv = p.hin << p.in_shift, wv = p.win << p.in_shift;
-    const int kwid = up ? 3 : p.kw;
-    const int total_chunks = my_tiles * num_kc;
-
-    auto load_rows = [&](TcRows& rs, int it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      if (rs.tile == tile) return;
-      rs.tile = tile;
-      const TcTile tt = tc_decode_tile(tile, m_tiles, n_tiles);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int b, oy, ox;
-        tc_row_pixel(p, (int64_t)tt.mt * TC_BM + r0 + 32 * i, m_total, tt.ph, b, oy, ox);
-        rs.b[i] = b;
-        rs.r[i] = tc_row_region(p, b, oy, ox);
-        if (up) {
-          rs.y[i] = (oy >> 1) - 1;
-          rs.x[i] = (ox >> 1) - 1;
-        } else {
-          rs.y[i] = oy * p.stride - p.pad;
-          rs.x[i] = ox * p.stride - p.pad;
-        }
-      }
-    };
-
-    float4 v0[4][2], v1[4][2];
-    uint32_t okm0 = 0, okm1 = 0;
-    TcRows rows0, rows1;
-    rows0.tile = rows1.tile = -1;
-
-    // issue the global loads of global chunk g into (v, okm), refreshing that buffer's row bookkeeping if needed
-    auto prefetch = [&](float4 (&v)[4][2], uint32_t& okm, TcRows& rs, int g) {
-      okm = 0;
-      if (g >= total_chunks) return;
-      const int it = g / num_kc, kc = g - it * num_kc;
-      load_rows(rs, it);
-      const int k0 = kc * TC_BK + cg * 8;
-      const int tap = k0 / p.cin;
-      const int ci = k0 - tap * p.cin;
-      const int ky = tap / kwid, kx = tap - ky * kwid;
-      if (k0 >= K) return;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int iy = rs.y[i] + ky, ix = rs.x[i] + kx;
-        if (rs.b[i] >= 0 && iy >= 0 && iy < hv && ix >= 0 && ix < wv) {
-          okm |= 1u << i;
-          iy >>= p.in_shift;
-          ix >>= p.in_shift;
-          const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)rs.b[i] * p.hin + iy) * p.win + ix) * p.x_pitch + ci);
-          v[i][0] = __ldg(src);
-          v[i][1] = __ldg(src + 1);
-        }
-      }
-    };
-    // normalise / modulate / split / store chunk g from (v, okm), then hand the stage to the MMA warp
-    auto consume = [&](float4 (&v)[4][2], uint32_t okm, const TcRows& rs, int g) {
-      const int s = g % STAGES;
-      const uint32_t par = (g / STAGES) & 1;
-      const int kc = g % num_kc;
-      mbar_wait(bar_empty + 8 * s, par ^ 1);
-      uint8_t* a_hi = smem + s * STAGE_BYTES;
-      uint8_t* a_lo = a_hi + TC_A_BYTES;
-      const int ci = (kc * TC_BK + cg * 8) % p.cin;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = r0 + 32 * i;
-        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (okm & (1u << i)) {
-          f[0] = v[i][0].x; f[1] = v[i][0].y; f[2] = v[i][0].z; f[3] = v[i][0].w;
-          f[4] = v[i][1].x; f[5] = v[i][1].y; f[6] = v[i][1].z; f[7] = v[i][1].w;
-          if (p.in_mean) {
-            const float4* mp = reinterpret_cast<const float4*>(p.in_mean + (int64_t)rs.b[i] * p.cin + ci);
-            const float4* qp = reinterpret_cast<const float4*>(p.in_rstd + (int64_t)rs.b[i] * p.cin + ci);
-            const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), q0 = __ldg(qp), q1 = __ldg(qp + 1);
-            f[0] = (f[0] - m0.x) * q0.x; f[1] = (f[1] - m0.y) * q0.y; f[2] = (f[2] - m0.z) * q0.z; f[3] = (f[3] - m0.w) * q0.w;
-            f[4] = (f[4] - m1.x) * q1.x; f[5] = (f[5] - m1.y) * q1.y; f[6] = (f[6] - m1.z) * q1.z; f[7] = (f[7] - m1.w) * q1.w;
-          }
-          if (p.smod) {
-            const float4* sp = reinterpret_cast<const float4*>(p.smod + ((int64_t)rs.b[i] * p.regions + rs.r[i]) * p.cin + ci);
-            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-          }
-        }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = f[2 * j], b = f[2 * j + 1];
-          const uint32_t h = pack_bf16x2(a, b);
-          hi[j] = h;
-          lo[j] = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
-        }
-        const uint32_t off = row * 128 + ((cg ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-    };
-
-    prefetch(v0, okm0, rows0, 0);
-    prefetch(v1, okm1, rows1, 1);
-    for (int g = 0; g < total_chunks; g += 2) {
-      consume(v0, okm0, rows0, g);
-      prefetch(v0, okm0, rows0, g + 2);
-      if (g + 1 < total_chunks) {
-        consume(v1, okm1, rows1, g + 1);
-        prefetch(v1, okm1, rows1, g + 3);
-      }
-    }
-  } else if (warp < TC2_MMA_WARP) {
-    // =========================== epilogue warpgroup ===============================================
-    const int q = warp & 3;
-    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
-    for (int it = 0; it < my_tiles; ++it) {
-      const TcTile tt = tc_decode_tile((int)blockIdx.x + it * (int)gridDim.x, m_tiles, n_tiles);
-      const int abuf = it & 1;
-      int b, oy, ox;
-      tc_row_pixel(p, (int64_t)tt.mt * TC_BM + q * 32 + lane, m_total, tt.ph, b, oy, ox);
-      const bool live = b >= 0;
-      const int reg = tc_row_region(p, b, oy, ox);
-      const int64_t pix = live ? ((int64_t)b * p.hout + oy) * p.wout + ox : 0;
-      const float* drow = (p.demod && live) ? p.demod + ((int64_t)b * p.regions + reg) * p.cout : nullptr;
-      float pw = 1.f;
-      if (p.pixw && live) {
-        const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
-        pw = __ldg(p.pixw + (int64_t)b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
-      }
-      const float* nrow = (p.noise && live) ? p.noise + (int64_t)b * p.noise_sb + (int64_t)oy * p.wout + ox : nullptr;
-      float nz_shared = 0.f;
-      if (nrow && p.noise_sc == 0) nz_shared = nw * __ldg(nrow);
-      mbar_wait(bar_acc_full + 8 * abuf, (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(abuf * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float acc[16];
-        tmem_ld16(tacc + (uint32_t)c0, acc);
-        if (!live) continue;
-        const int n0 = tt.nt * BN + c0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + j;
-          float t = acc[j];
-          if (drow) t *= __ldg(drow + n);
-          if (p.pixw) t *= pw;
-          if (p.ch_scale) t *= __ldg(p.ch_scale + n);
-          if (nrow) t += (p.noise_sc == 0) ? nz_shared : nw * __ldg(nrow + (int64_t)n * p.noise_sc);
-          if (p.ch_shift) t += __ldg(p.ch_shift + n);
-          if (p.res && !p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
-          switch (p.act) {
-            case E4S_ACT_LRELU: t = (t < 0.f ? t * p.act_slope : t) * p.act_gain; break;
-            case E4S_ACT_RELU: t = fmaxf(t, 0.f); break;
-            case E4S_ACT_PRELU: t = t < 0.f ? t * __ldg(p.act_prelu + n) : t; break;
-            case E4S_ACT_SIGMOID: t = 1.f / (1.f + expf(-t)); break;
-            case E4S_ACT_RSQRT_EPS: t = rsqrtf(t + p.act_slope); break;
-            default: break;
-          }
-          if (p.res && p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
-          acc[j] = t;
-        }
-        float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_pitch + n0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 val = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          if (p.accumulate) {
-            const float4 old = o[j];
-            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-          }
-          o[j] = val;
-        }
-      }
-      tc_fence_before();                       // TMEM reads of this buffer are done
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * abuf);
-    }
-  } else if (warp == TC2_MMA_WARP) {
-    // =========================== MMA issuer ======================================================
-    if (lane == 0) {
-      int g = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int abuf = it & 1;
-        mbar_wait(bar_acc_empty + 8 * abuf, ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(abuf * BN);
-        for (int kc = 0; kc < num_kc; ++kc, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(bar_full + 8 * s, (g / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
-          const uint32_t b_hi = a_lo + TC_A_BYTES, b_lo = b_hi + B_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint32_t koff = k * 32;
-            const uint64_t dah = umma_smem_desc(a_hi + koff), dal = umma_smem_desc(a_lo + koff);
-            const uint64_t dbh = umma_smem_desc(b_hi + koff), dbl = umma_smem_desc(b_lo + koff);
-            umma_bf16(tacc, dal, dbh, IDESC, (kc | k) != 0);
-            umma_bf16(tacc, dah, dbl, IDESC, 1);
-            umma_bf16(tacc, dah, dbh, IDESC, 1);
-          }
-          umma_commit(bar_empty + 8 * s);
-        }
-        umma_commit(bar_acc_full + 8 * abuf);
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================== weight loader ====================================================
-    if (lane == 0) {
-      const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
-      int g = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const TcTile tt = tc_decode_tile((int)blockIdx.x + it * (int)gridDim.x, m_tiles, n_tiles);
-        const uint8_t* src = wpk + ((int64_t)tt.ph * n_tiles + tt.nt) * num_kc * tile_bytes;
-        for (int kc = 0; kc < num_kc; ++kc, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(bar_empty + 8 * s, ((g / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_BYTES);
-          bulk_g2s(smem_base + s * STAGE_BYTES + 2 * TC_A_BYTES, src + kc * tile_bytes, 2 * B_BYTES, bar_full + 8 * s);
-        }
-      }
-    }
-    __syncwarp();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == TC2_MMA_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
 int validate_conv(const E4SConv* p);
 
-static int g_tc_persistent = -1;   // -1: read E4S_TC_PERSISTENT (default off: v2 measured slower than v1)
 static int g_tc_halo = -1;         // -1: read E4S_TC_HALO (default on)
 bool tc_halo_eligible(const E4SConv* p);
 int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s);
-static int g_sm_count = 0;
 
 static bool tc_shape_ok(int k, int cout) {
   if (k < 8 || k % 8) return false;
@@ -682,37 +308,7 @@ static bool tc_shape_ok(int k, int cout) {
 }
 
 template <int BN>
-static int launch_tc_persist(const E4SConv* p, const void* wpk, int64_t m_total, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes(BN));
-    if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
-  const int64_t m_tiles = ceil_div64(m_total, TC_BM);
-  const int n_tiles = p->cout / BN;
-  const int64_t total = m_tiles * n_tiles * (up ? 4 : 1);
-  E4S_REQUIRE(total < 0x7fffffff, "conv_tc: too many tiles");
-  const unsigned grid = (unsigned)(total < g_sm_count ? total : g_sm_count);
-  conv_tc_persist_kernel<BN><<<grid, TC2_THREADS, tc2_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, (int)m_tiles,
-                                                                           n_tiles, (int)total);
-  return check_launch("e4s_conv_tc(persistent)");
-}
-
-template <int BN>
 static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStream_t s) {
-  if (g_tc_persistent < 0) {
-    const char* e = getenv("E4S_TC_PERSISTENT");
-    g_tc_persistent = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (g_tc_persistent) return launch_tc_persist<BN>(p, wpk, m_total, s);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
@@ -756,6 +352,8 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc: out must be 16-byte aligned with pitch %% 4 == 0");
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
   if (p->smod) E4S_REQUIRE((reinterpret_cast<uintptr_t>(p->smod) & 15) == 0, "conv_tc: smod must be 16-byte aligned");
+  if (p->res) E4S_REQUIRE(p->res_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->res) & 15) == 0, "conv_tc: res must be 16-byte aligned with pitch %% 4 == 0");
+  if (p->demod) E4S_REQUIRE((reinterpret_cast<uintptr_t>(p->demod) & 15) == 0, "conv_tc: demod must be 16-byte aligned");
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   const int64_t m_total = up ? (int64_t)p->batch * p->hin * p->win : (int64_t)p->batch * p->hout * p->wout;
   cudaStream_t s = as_stream(stream);

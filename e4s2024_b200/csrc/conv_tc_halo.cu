@@ -28,7 +28,7 @@ constexpr int HL_HPIX = (HL_TH + 2) * HL_HP;      // 180 halo pixels
 constexpr int HL_PLANE = 23 * 1024;               // one bf16 plane (hi or lo): 180 * 128 B rounded up to 1 KB
 constexpr int HL_HALO_STAGES = 2;
 constexpr int HL_THREADS = 14 * 32;
-constexpr int HL_EPI_WARP0 = 8, HL_MMA_WARP = 12, HL_LOAD_WARP = 13;
+constexpr int HL_MMA_WARP = 12;             // warps 8-11 epilogue, 12 MMA issuer, 13 weight loader
 constexpr int HL_ITEMS = (HL_HPIX + 31) / 32;     // 6 (pixel, 8-channel) items per producer thread
 
 __host__ __device__ constexpr int hl_b_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 4 : 6); }
@@ -206,58 +206,36 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       const HlJob jb = decode(it);
       const int set = nsets == 2 ? (it & 1) : 0;
       const int use = nsets == 2 ? (it >> 1) : it;
-      mbar_wait(bar_afull + 8 * set, use & 1);
-      tc_fence_after();
+      // per-pixel epilogue operands (noise / float-mask loads) are fetched BEFORE waiting for the accumulator
       const float* drow = p.demod ? p.demod + (int64_t)jb.b * p.regions * p.cout : nullptr;
-      for (int ph = 0; ph < P; ++ph) {
+      TcEpiRow er[4];
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) {
+        if (ph >= P) break;
         const int oy = up ? 2 * (jb.y0 + ty) + (ph >> 1) : jb.y0 + ty;
         const int ox = up ? 2 * (jb.x0 + tx) + (ph & 1) : jb.x0 + tx;
-        const int64_t pix = ((int64_t)jb.b * p.hout + oy) * p.wout + ox;
-        float pw = 1.f;
+        er[ph].pix = ((int64_t)jb.b * p.hout + oy) * p.wout + ox;
+        er[ph].drow = drow;
+        er[ph].pw = 1.f;
         if (p.pixw) {
           const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
-          pw = __ldg(p.pixw + (int64_t)jb.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
+          er[ph].pw = __ldg(p.pixw + (int64_t)jb.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
         }
-        const float* nrow = p.noise ? p.noise + (int64_t)jb.b * p.noise_sb + (int64_t)oy * p.wout + ox : nullptr;
-        float nz_shared = 0.f;
-        if (nrow && p.noise_sc == 0) nz_shared = nw * __ldg(nrow);
+        er[ph].nw = nw;
+        er[ph].nrow = p.noise ? p.noise + (int64_t)jb.b * p.noise_sb + (int64_t)oy * p.wout + ox : nullptr;
+        er[ph].nz = (er[ph].nrow && p.noise_sc == 0) ? nw * __ldg(er[ph].nrow) : 0.f;
+      }
+      mbar_wait(bar_afull + 8 * set, use & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) {
+        if (ph >= P) break;
         const uint32_t tacc = tmem_base + (uint32_t)((set * P + ph) * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float acc[16];
           tmem_ld16(tacc + (uint32_t)c0, acc);
-          const int n0 = jb.nt * BN + c0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + j;
-            float t = acc[j];
-            if (drow) t *= __ldg(drow + n);
-            if (p.pixw) t *= pw;
-            if (p.ch_scale) t *= __ldg(p.ch_scale + n);
-            if (nrow) t += (p.noise_sc == 0) ? nz_shared : nw * __ldg(nrow + (int64_t)n * p.noise_sc);
-            if (p.ch_shift) t += __ldg(p.ch_shift + n);
-            if (p.res && !p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
-            switch (p.act) {
-              case E4S_ACT_LRELU: t = (t < 0.f ? t * p.act_slope : t) * p.act_gain; break;
-              case E4S_ACT_RELU: t = fmaxf(t, 0.f); break;
-              case E4S_ACT_PRELU: t = t < 0.f ? t * __ldg(p.act_prelu + n) : t; break;
-              case E4S_ACT_SIGMOID: t = 1.f / (1.f + expf(-t)); break;
-              case E4S_ACT_RSQRT_EPS: t = rsqrtf(t + p.act_slope); break;
-              default: break;
-            }
-            if (p.res && p.res_after_act) t += __ldg(p.res + pix * p.res_pitch + n);
-            acc[j] = t;
-          }
-          float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_pitch + n0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 val = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            if (p.accumulate) {
-              const float4 old = o[j];
-              val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-            }
-            o[j] = val;
-          }
+          tc_epilogue16(p, acc, jb.nt * BN + c0, er[ph]);
         }
       }
       tc_fence_before();

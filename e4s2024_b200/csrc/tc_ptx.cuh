@@ -118,5 +118,88 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fused epilogue for one accumulator row (one output pixel) x 16 consecutive channels, shared by the tcgen05
+// kernels.  Per-channel vectors are read with 16-byte read-only loads (L1 resident), the pixel's 16 outputs leave
+// as four st.global.v4.  Kept compact on purpose: the first version unrolled ~40 scalar instructions per element
+// and the epilogue warps became the bottleneck of the small-N layers (profiles/r1_ncu_halo_v1_stalls.txt).
+// ---------------------------------------------------------------------------------------------------
+struct TcEpiRow {
+  const float* drow;     // demodulation row (b, region) or nullptr
+  const float* nrow;     // noise plane pointer at this pixel (channel 0) or nullptr
+  float pw;              // float-mask weight (generic path) when p.pixw
+  float nz;              // noise_w * noise[pixel] when the noise has one channel
+  float nw;              // noise weight
+  int64_t pix;           // output pixel index
+};
+
+__device__ __forceinline__ float4 ldg4(const float* ptr) { return __ldg(reinterpret_cast<const float4*>(ptr)); }
+
+__device__ __forceinline__ float tc_act(float t, int act, float slope, float gain) {
+  switch (act) {
+    case E4S_ACT_LRELU: return (t < 0.f ? t * slope : t) * gain;
+    case E4S_ACT_RELU: return fmaxf(t, 0.f);
+    case E4S_ACT_SIGMOID: return 1.f / (1.f + expf(-t));
+    case E4S_ACT_RSQRT_EPS: return rsqrtf(t + slope);
+    default: return t;
+  }
+}
+
+__device__ __forceinline__ void tc_epilogue16(const E4SConv& p, const float (&acc)[16], const int n0, const TcEpiRow& r) {
+  float4* o = reinterpret_cast<float4*>(p.out + r.pix * p.out_pitch + n0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = n0 + 4 * q;
+    float4 a = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    if (r.drow) {
+      const float4 d = ldg4(r.drow + n);
+      a.x *= d.x; a.y *= d.y; a.z *= d.z; a.w *= d.w;
+    }
+    if (p.pixw) {
+      a.x *= r.pw; a.y *= r.pw; a.z *= r.pw; a.w *= r.pw;
+    }
+    if (p.ch_scale) {
+      const float4 s = ldg4(p.ch_scale + n);
+      a.x *= s.x; a.y *= s.y; a.z *= s.z; a.w *= s.w;
+    }
+    if (r.nrow) {
+      if (p.noise_sc == 0) {
+        a.x += r.nz; a.y += r.nz; a.z += r.nz; a.w += r.nz;
+      } else {
+        a.x += r.nw * __ldg(r.nrow + (int64_t)n * p.noise_sc);
+        a.y += r.nw * __ldg(r.nrow + (int64_t)(n + 1) * p.noise_sc);
+        a.z += r.nw * __ldg(r.nrow + (int64_t)(n + 2) * p.noise_sc);
+        a.w += r.nw * __ldg(r.nrow + (int64_t)(n + 3) * p.noise_sc);
+      }
+    }
+    if (p.ch_shift) {
+      const float4 s = ldg4(p.ch_shift + n);
+      a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+    }
+    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.res) {
+      rs = ldg4(p.res + r.pix * p.res_pitch + n);
+      if (!p.res_after_act) {
+        a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
+      }
+    }
+    if (p.act == E4S_ACT_PRELU) {
+      const float4 s = ldg4(p.act_prelu + n);
+      a.x = a.x < 0.f ? a.x * s.x : a.x; a.y = a.y < 0.f ? a.y * s.y : a.y;
+      a.z = a.z < 0.f ? a.z * s.z : a.z; a.w = a.w < 0.f ? a.w * s.w : a.w;
+    } else if (p.act != E4S_ACT_NONE) {
+      a.x = tc_act(a.x, p.act, p.act_slope, p.act_gain); a.y = tc_act(a.y, p.act, p.act_slope, p.act_gain);
+      a.z = tc_act(a.z, p.act, p.act_slope, p.act_gain); a.w = tc_act(a.w, p.act, p.act_slope, p.act_gain);
+    }
+    if (p.res && p.res_after_act) {
+      a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
+    }
+    if (p.accumulate) {
+      const float4 old = o[q];
+      a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
+    }
+    o[q] = a;
+  }
+}
 
 }  // namespace e4s
