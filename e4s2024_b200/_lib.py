@@ -45,8 +45,8 @@ class E4SConv(C.Structure):
 
 
 EXPORTS = [
-    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_tc",
-    "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc",
+    "e4s_debug_halo_trace", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
@@ -113,6 +113,13 @@ def conv(params: E4SConv, tc_weights: Optional[torch.Tensor] = None):
         _check(lib().e4s_conv_tc(C.byref(params), C.c_void_p(tc_weights.data_ptr()), _stream()), "e4s_conv_tc")
     else:
         _check(lib().e4s_conv_f32(C.byref(params), _stream()), "e4s_conv_f32")
+
+
+def conv_batched(params_list):
+    """Launch a list of E4SConv problems (mode NORMAL, fp32 engine) as one batched kernel."""
+    n = len(params_list)
+    arr = (E4SConv * n)(*params_list)
+    _check(lib().e4s_conv_f32_batched(arr, n, _stream()), "e4s_conv_f32_batched")
 
 
 def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cout: int, cout_pad: int) -> torch.Tensor:

@@ -29,7 +29,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope, float 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const E4SConv p, const int64_t m_total) {
+__device__ __forceinline__ void conv_igemm_f32_body(const E4SConv& p, const int64_t m_total, const int bx, const int by, const int phase) {
   constexpr int NH = BN / 64;  // column halves handled per thread (4 columns each)
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + APAD];
@@ -37,9 +37,8 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const E4SConv p, co
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int phase = blockIdx.z;
   const int py = phase >> 1, px = phase & 1;
-  const int n0 = blockIdx.y * BN;
+  const int n0 = by * BN;
   const int K = p.kh * p.kw * p.cin;
   const float* wbase = p.w + (int64_t)phase * K * p.cout_pad;
 
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const E4SConv p, co
   const int ghalf = tid >> 7;
   int gb = -1, goy = 0, gox = 0, gr = 0, ga = 0, gbb = 0;
   {
-    int64_t m = (int64_t)blockIdx.x * BM + gm;
+    int64_t m = (int64_t)bx * BM + gm;
     if (m < m_total) {
       if (p.mode == E4S_CONV_UP2_POLYPHASE) {
         int hw = p.hin * p.win;
@@ -239,6 +238,27 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const E4SConv p, co
   }
 }
 
+template <int BN>
+__global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const E4SConv p, const int64_t m_total) {
+  conv_igemm_f32_body<BN>(p, m_total, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Batched launch of up to CONV_BATCH_MAX independent (mode NORMAL) problems in ONE kernel: blockIdx.z picks the
+// problem.  Used for the per-forward style tables (26 modulation + 17 demodulation GEMMs of a Generator forward were
+// 43 tiny launches = 8.5 % of the step, profiles/r1_launches_tc_halo.txt).
+constexpr int CONV_BATCH_MAX = 32;
+struct ConvBatch {
+  E4SConv c[CONV_BATCH_MAX];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256) conv_igemm_f32_batched_kernel(const __grid_constant__ ConvBatch batch) {
+  const E4SConv& p = batch.c[blockIdx.z];
+  const int64_t m_total = (int64_t)p.batch * p.hout * p.wout;
+  if ((int64_t)blockIdx.x * BM >= m_total || (int)blockIdx.y * BN >= p.cout) return;
+  conv_igemm_f32_body<BN>(p, m_total, blockIdx.x, blockIdx.y, 0);
+}
+
 int validate_conv(const E4SConv* p) {
   E4S_REQUIRE(p != nullptr, "conv: null params");
   E4S_REQUIRE(p->x && p->w && p->out, "conv: null x/w/out");
@@ -286,4 +306,31 @@ extern "C" int e4s_conv_f32(const E4SConv* p, void* stream) {
     conv_igemm_f32_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(*p, m_total);
   }
   return check_launch("e4s_conv_f32");
+}
+
+extern "C" int e4s_conv_f32_batched(const E4SConv* params, int count, void* stream) {
+  using namespace e4s;
+  E4S_REQUIRE(params && count > 0, "conv_f32_batched: empty batch");
+  cudaStream_t s = as_stream(stream);
+  for (int base = 0; base < count; base += CONV_BATCH_MAX) {
+    const int n = count - base < CONV_BATCH_MAX ? count - base : CONV_BATCH_MAX;
+    ConvBatch batch;
+    int64_t max_mt = 1;
+    int max_cout = 1;
+    for (int i = 0; i < n; ++i) {
+      int rc = validate_conv(&params[base + i]);
+      if (rc) return rc;
+      E4S_REQUIRE(params[base + i].mode == E4S_CONV_NORMAL, "conv_f32_batched: only E4S_CONV_NORMAL problems");
+      batch.c[i] = params[base + i];
+      const int64_t mt = ceil_div64((int64_t)params[base + i].batch * params[base + i].hout * params[base + i].wout, BM);
+      if (mt > max_mt) max_mt = mt;
+      if (params[base + i].cout > max_cout) max_cout = params[base + i].cout;
+    }
+    E4S_REQUIRE(max_mt <= 0x7fffffff, "conv_f32_batched: too many tiles");
+    dim3 grid((unsigned)max_mt, (unsigned)ceil_div(max_cout, 128), (unsigned)n);
+    conv_igemm_f32_batched_kernel<128><<<grid, 256, 0, s>>>(batch);
+    int rc = check_launch("e4s_conv_f32_batched");
+    if (rc) return rc;
+  }
+  return E4S_OK;
 }

@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
           iy >>= p.in_shift;
           ix >>= p.in_shift;
           const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)rb[i] * p.hin + iy) * p.win + ix) * p.x_pitch + ci);
-          v[i][0] = __ldg(src);
-          v[i][1] = __ldg(src + 1);
+          v[i][0] = ldg_stream4(src);
+          v[i][1] = ldg_stream4(src + 1);
         }
       }
     };
@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     }
     tc_fence_before();
   } else if (warp == TC_PRODUCER_WARPS) {
-    // =========================== MMA issuer ======================================================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp walks the loop, one elected lane issues) ====
+    {
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % STAGES;
         const uint32_t par = (kc / STAGES) & 1;
@@ -229,23 +229,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         tc_fence_after();
         const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
         const uint32_t b_hi = a_lo + TC_A_BYTES, b_lo = b_hi + B_BYTES;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
-          const uint64_t dah = umma_smem_desc(a_hi + koff), dal = umma_smem_desc(a_lo + koff);
-          const uint64_t dbh = umma_smem_desc(b_hi + koff), dbl = umma_smem_desc(b_lo + koff);
-          umma_bf16(tmem_acc, dal, dbh, IDESC, (kc | k) != 0);   // small terms first
-          umma_bf16(tmem_acc, dah, dbl, IDESC, 1);
-          umma_bf16(tmem_acc, dah, dbh, IDESC, 1);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+            const uint64_t dah = umma_smem_desc(a_hi + koff), dal = umma_smem_desc(a_lo + koff);
+            const uint64_t dbh = umma_smem_desc(b_hi + koff), dbl = umma_smem_desc(b_lo + koff);
+            umma_bf16(tmem_acc, dal, dbh, IDESC, (kc | k) != 0);   // small terms first
+            umma_bf16(tmem_acc, dah, dbl, IDESC, 1);
+            umma_bf16(tmem_acc, dah, dbh, IDESC, 1);
+          }
+          umma_commit(bar_empty + 8 * s);          // frees this smem stage once the MMAs above have read it
         }
-        umma_commit(bar_empty + 8 * s);          // frees this smem stage once the MMAs above have read it
+        __syncwarp();
       }
-      umma_commit(bar_acc);                      // accumulator complete -> epilogue
+      if (elect_one()) umma_commit(bar_acc);       // accumulator complete -> epilogue
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // =========================== B loader (bulk-copy engine) ======================================
-    if (lane == 0) {
+    {
       const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
       const uint8_t* src = wpk + ((int64_t)phase_id * gridDim.y + n_tile) * num_kc * tile_bytes;
       for (int kc = 0; kc < num_kc; ++kc) {
@@ -253,11 +256,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         const uint32_t par = (kc / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, par ^ 1);
         const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * TC_A_BYTES;
-        mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_BYTES);
-        bulk_g2s(dst, src + kc * tile_bytes, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous in the packed image
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_BYTES);
+          bulk_g2s(dst, src + kc * tile_bytes, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous in the packed image
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
 
   __syncthreads();

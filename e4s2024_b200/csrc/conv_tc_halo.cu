@@ -44,6 +44,19 @@ struct HlJob {
   int b, y0, x0, nt;
 };
 
+// optional timeline trace of CTA 0 (debug / profiling aid): records (role, job, event, clock64) when a buffer is installed
+__device__ unsigned long long* g_hl_trace = nullptr;
+__device__ int g_hl_trace_cap = 0;
+__device__ int g_hl_trace_n = 0;
+__device__ __forceinline__ void hl_trace(int role, int it, int ev) {
+  if (g_hl_trace == nullptr || blockIdx.x != 0) return;
+  const int i = atomicAdd(&g_hl_trace_n, 1);
+  if (i < g_hl_trace_cap) {
+    g_hl_trace[2 * i] = ((unsigned long long)role << 48) | ((unsigned long long)(it & 0xffffff) << 16) | (unsigned long long)ev;
+    g_hl_trace[2 * i + 1] = clock64();
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
@@ -148,8 +161,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         if (px < HL_HPIX && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
           okm |= 1u << i;
           const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)jb.b * p.hin + iy) * p.win + ix) * p.x_pitch + ch);
-          v[i][0] = __ldg(src);
-          v[i][1] = __ldg(src + 1);
+          v[i][0] = ldg_stream4(src);
+          v[i][1] = ldg_stream4(src + 1);
         }
       }
     };
@@ -157,7 +170,9 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     prefetch(0);
     for (int hg = 0; hg < total_hg; ++hg) {
       const int hs = hg & 1;
+      if (tid == 0) hl_trace(0, hg, 0);
       mbar_wait(bar_hempty + 8 * hs, ((hg >> 1) & 1) ^ 1);
+      if (tid == 0) hl_trace(0, hg, 1);
       uint8_t* h_hi = smem + hs * HALO_BYTES;
       uint8_t* h_lo = h_hi + HL_PLANE;
       if (cg_live) {
@@ -191,10 +206,12 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
+      if (tid == 0) hl_trace(0, hg, 2);
       prefetch(hg + 1);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
+      if (tid == 0) hl_trace(0, hg, 3);
     }
   } else if (warp < HL_MMA_WARP) {
     // =========================== epilogue warpgroup ===============================================
@@ -225,8 +242,10 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         er[ph].nrow = p.noise ? p.noise + (int64_t)jb.b * p.noise_sb + (int64_t)oy * p.wout + ox : nullptr;
         er[ph].nz = (er[ph].nrow && p.noise_sc == 0) ? nw * __ldg(er[ph].nrow) : 0.f;
       }
+      if (warp == 8 && lane == 0) hl_trace(1, it, 0);
       mbar_wait(bar_afull + 8 * set, use & 1);
       tc_fence_after();
+      if (warp == 8 && lane == 0) hl_trace(1, it, 1);
 #pragma unroll
       for (int ph = 0; ph < 4; ++ph) {
         if (ph >= P) break;
@@ -241,19 +260,23 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_aempty + 8 * set);
+      if (warp == 8 && lane == 0) hl_trace(1, it, 2);
     }
   } else if (warp == HL_MMA_WARP) {
-    // =========================== MMA issuer ======================================================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ==
+    {
       int hg = 0, bc = 0;                                    // running halo-fill and weight-chunk counters
       for (int it = 0; it < my_jobs; ++it) {
         const int set = nsets == 2 ? (it & 1) : 0;
         const int use = nsets == 2 ? (it >> 1) : it;
+        if (lane == 0) hl_trace(2, it, 0);
         mbar_wait(bar_aempty + 8 * set, (use & 1) ^ 1);
         tc_fence_after();
+        if (lane == 0) hl_trace(2, it, 1);
         for (int g = 0; g < G; ++g, ++hg) {
           const int hs = hg & 1;
           mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
+          if (lane == 0) hl_trace(2, it, 2);
           tc_fence_after();
           const uint32_t h_hi = smem_base + hs * HALO_BYTES, h_lo = h_hi + HL_PLANE;
           for (int ph = 0; ph < P; ++ph) {
@@ -268,27 +291,34 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
                 if (tap >= 9) break;
                 const uint32_t aoff = (uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u;
                 const uint32_t boff = (uint32_t)(tt * cin_eff * 2);
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t dah = umma_smem_desc_sbo(h_hi + aoff + k * 32, HL_HP * 128);
-                  const uint64_t dal = umma_smem_desc_sbo(h_lo + aoff + k * 32, HL_HP * 128);
-                  const uint64_t dbh = umma_smem_desc(b_hi + boff + k * 32), dbl = umma_smem_desc(b_lo + boff + k * 32);
-                  umma_bf16(tacc, dal, dbh, IDESC, (g | tap | k) != 0);
-                  umma_bf16(tacc, dah, dbl, IDESC, 1);
-                  umma_bf16(tacc, dah, dbh, IDESC, 1);
+                if (elect_one()) {
+                  for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t dah = umma_smem_desc_sbo(h_hi + aoff + k * 32, HL_HP * 128);
+                    const uint64_t dal = umma_smem_desc_sbo(h_lo + aoff + k * 32, HL_HP * 128);
+                    const uint64_t dbh = umma_smem_desc(b_hi + boff + k * 32), dbl = umma_smem_desc(b_lo + boff + k * 32);
+                    umma_bf16(tacc, dal, dbh, IDESC, (g | tap | k) != 0);
+                    umma_bf16(tacc, dah, dbl, IDESC, 1);
+                    umma_bf16(tacc, dah, dbh, IDESC, 1);
+                  }
                 }
+                __syncwarp();
               }
-              umma_commit(bar_bempty + 8 * bs);
+              if (elect_one()) umma_commit(bar_bempty + 8 * bs);
+              __syncwarp();
             }
           }
-          umma_commit(bar_hempty + 8 * hs);                  // every tap of every phase has read this halo
+          if (elect_one()) umma_commit(bar_hempty + 8 * hs);  // every tap of every phase has read this halo
+          __syncwarp();
         }
-        umma_commit(bar_afull + 8 * set);
+        if (elect_one()) umma_commit(bar_afull + 8 * set);
+        __syncwarp();
+        if (lane == 0) hl_trace(2, it, 3);
       }
     }
     __syncwarp();
   } else {
     // =========================== weight loader ====================================================
-    if (lane == 0) {
+    {
       const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
       int bc = 0;
       for (int it = 0; it < my_jobs; ++it) {
@@ -300,8 +330,11 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               const int bs = bc % BST;
               const int kc = tpc == 1 ? c * G + g : c;       // packed chunk = k / 64 with k = tap*cin + ci
               mbar_wait(bar_bempty + 8 * bs, ((bc / BST) & 1) ^ 1);
-              mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * B_BYTES);
-              bulk_g2s(smem_base + B_OFF + bs * 2 * B_BYTES, src + kc * tile_bytes, 2 * B_BYTES, bar_bfull + 8 * bs);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * B_BYTES);
+                bulk_g2s(smem_base + B_OFF + bs * 2 * B_BYTES, src + kc * tile_bytes, 2 * B_BYTES, bar_bfull + 8 * bs);
+              }
+              __syncwarp();
             }
           }
       }
@@ -354,6 +387,15 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
   return check_launch("e4s_conv_tc(halo)");
 }
 
+int tc_halo_set_trace(void* buf, int cap_records) {
+  unsigned long long* ptr = static_cast<unsigned long long*>(buf);
+  int zero = 0;
+  cudaError_t e = cudaMemcpyToSymbol(g_hl_trace, &ptr, sizeof(ptr));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_hl_trace_cap, &cap_records, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_hl_trace_n, &zero, sizeof(int));
+  return e == cudaSuccess ? E4S_OK : fail(E4S_ERR_CUDA, "halo trace: %s", cudaGetErrorString(e));
+}
+
 int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
   switch (tc_block_n(p->cout)) {
     case 256: return launch_halo<256>(p, wpk, s);
@@ -365,3 +407,6 @@ int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
 }
 
 }  // namespace e4s
+
+// debug aid (not part of the reference-facing surface): install / remove a clock64 timeline buffer for CTA 0 of the halo kernel
+extern "C" int e4s_debug_halo_trace(void* buf, int cap_records) { return e4s::tc_halo_set_trace(buf, cap_records); }

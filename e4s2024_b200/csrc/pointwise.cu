@@ -204,9 +204,14 @@ __global__ void labels_to_onehot_kernel(const uint8_t* __restrict__ labels, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip, NHWC in -> NCHW out
-// LP lanes cooperate on one pixel (float4 channel slices), warp-shuffle reduction.
+// ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip, NHWC in -> NCHW out.
+// A CTA owns TORGB_TILE consecutive pixels.  Phase A: LP lanes cooperate on one pixel (coalesced float4 channel
+// slices, warp-shuffle reduction) and park the three dot products in shared memory.  Phase B: one thread per pixel
+// adds bias and the 2x2 non-zero taps of the zero-insert-upsampled skip (closed form of upfirdn2d(up=2, pad=(2,1)))
+// and writes the three NCHW planes fully coalesced.
 // ------------------------------------------------------------------------------------------------
+constexpr int TORGB_TILE = 256;
+
 template <int LP>
 __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, int64_t x_pitch, int64_t npix, int h, int w,
                                                     int cin, const float* __restrict__ smod, const float* __restrict__ wrgb,
@@ -215,37 +220,33 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ bias, const float* __restrict__ skip,
                                                     const float* __restrict__ fir, float* __restrict__ rgb, int accumulate) {
   constexpr int PPW = 32 / LP;  // pixels per warp step
-  const int lane = threadIdx.x & 31;
+  __shared__ float srgb[3][TORGB_TILE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LP, ll = lane % LP;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int hw = h * w;
-  for (int64_t base = warp * PPW; base < npix; base += nwarps * PPW) {
-    const int64_t pix = base + sub;
+  const int64_t tile0 = (int64_t)blockIdx.x * TORGB_TILE;
+  // ---- phase A: dot products ---------------------------------------------------------------------
+  for (int t = warp * PPW + sub; t < TORGB_TILE; t += 8 * PPW) {       // whole warp iterates together (t differs by sub only)
+    const int64_t pix = tile0 + t;
     const bool ok = pix < npix;
-    int b = 0, y = 0, xx = 0, r = 0, sy = 0, sx = 0;
-    if (ok) {
-      b = (int)(pix / hw);
-      int rem = (int)(pix - (int64_t)b * hw);
-      y = rem / w;
-      xx = rem - y * w;
-      if (labels || pixw) {
-        sy = nearest_src(y, lab_h, h);
-        sx = nearest_src(xx, lab_w, w);
-      }
-      if (labels) r = labels[((int64_t)b * lab_h + sy) * lab_w + sx];
-    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (ok) {
+      const int b = (int)(pix / hw);
+      int r = 0;
+      if (labels) {
+        const int rem = (int)(pix - (int64_t)b * hw);
+        const int y = rem / w, xx = rem - y * w;
+        r = labels[((int64_t)b * lab_h + nearest_src(y, lab_h, h)) * lab_w + nearest_src(xx, lab_w, w)];
+      }
       const float* xr = x + pix * x_pitch;
       const float* sr = smod + ((int64_t)b * regions + r) * cin;
       for (int ci = ll * 4; ci < cin; ci += LP * 4) {
         float4 v = __ldg(reinterpret_cast<const float4*>(xr + ci));
         const float4 sm = __ldg(reinterpret_cast<const float4*>(sr + ci));
         v.x *= sm.x; v.y *= sm.y; v.z *= sm.z; v.w *= sm.w;
-        float4 w0 = __ldg(reinterpret_cast<const float4*>(wrgb + ci));
-        float4 w1 = __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci));
-        float4 w2 = __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrgb + ci));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci));
+        const float4 w2 = __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci));
         a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
         a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
         a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
@@ -257,35 +258,52 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
       a1 += __shfl_xor_sync(0xffffffffu, a1, o);
       a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
-    if (ok && ll < 3) {
-      const int c = ll;
-      float v = c == 0 ? a0 : (c == 1 ? a1 : a2);
-      if (pixw) v *= __ldg(pixw + (int64_t)b * pixw_sb + (int64_t)sy * lab_w + sx);
-      float* o = rgb + ((int64_t)b * 3 + c) * hw + (int64_t)y * w + xx;
-      if (accumulate) {
-        *o += v;
-      } else {
-        if (bias) v += __ldg(bias + c);
-        if (skip) {  // Upsample: zero-insert x2, pad (2,1), correlate with the flipped 4x4 FIR
-          const int sh = h >> 1, sw = w >> 1;
-          const float* sp = skip + ((int64_t)b * 3 + c) * sh * sw;
-          float u = 0.f;
-#pragma unroll
-          for (int ky = 0; ky < 4; ++ky) {
-            int uy = y - 2 + ky;
-            if (uy < 0 || (uy & 1) || (uy >> 1) >= sh) continue;
-#pragma unroll
-            for (int kx = 0; kx < 4; ++kx) {
-              int ux = xx - 2 + kx;
-              if (ux < 0 || (ux & 1) || (ux >> 1) >= sw) continue;
-              u = fmaf(__ldg(sp + (int64_t)(uy >> 1) * sw + (ux >> 1)), __ldg(fir + (3 - ky) * 4 + (3 - kx)), u);
-            }
-          }
-          v += u;
-        }
-        *o = v;
-      }
+    if (ll == 0) {
+      srgb[0][t] = a0;
+      srgb[1][t] = a1;
+      srgb[2][t] = a2;
     }
+  }
+  __syncthreads();
+  // ---- phase B: bias + skip + coalesced NCHW store -------------------------------------------------
+  const int t = threadIdx.x;
+  const int64_t pix = tile0 + t;
+  if (pix >= npix) return;
+  const int b = (int)(pix / hw);
+  const int rem = (int)(pix - (int64_t)b * hw);
+  const int y = rem / w, xx = rem - y * w;
+  float pw = 1.f;
+  if (pixw) pw = __ldg(pixw + (int64_t)b * pixw_sb + (int64_t)nearest_src(y, lab_h, h) * lab_w + nearest_src(xx, lab_w, w));
+  // skip taps: zero-inserted row u = y - 2 + ky is non-zero only for even u  ->  ky in {y&1, (y&1)+2}
+  const int sh = h >> 1, sw = w >> 1;
+  const int ky0 = y & 1, kx0 = xx & 1;
+  const int sy0 = (y - 2 + ky0) >> 1, sx0 = (xx - 2 + kx0) >> 1;     // arithmetic shift: -1 for the top/left border
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = srgb[c][t] * pw;
+    float* o = rgb + ((int64_t)b * 3 + c) * hw + rem;
+    if (accumulate) {
+      *o += v;
+      continue;
+    }
+    if (bias) v += __ldg(bias + c);
+    if (skip) {
+      const float* sp = skip + ((int64_t)b * 3 + c) * sh * sw;
+      float u = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int sy = sy0 + a, ky = ky0 + 2 * a;
+        if (sy < 0 || sy >= sh) continue;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const int sx = sx0 + d, kx = kx0 + 2 * d;
+          if (sx < 0 || sx >= sw) continue;
+          u = fmaf(__ldg(sp + (int64_t)sy * sw + sx), __ldg(fir + (3 - ky) * 4 + (3 - kx)), u);
+        }
+      }
+      v += u;
+    }
+    *o = v;
   }
 }
 
@@ -392,14 +410,15 @@ extern "C" int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, 
   E4S_REQUIRE(regions > 0 && (!(labels || pixw) || (lab_h > 0 && lab_w > 0)), "torgb: bad region args");
   int64_t npix = (int64_t)batch * h * w;
   cudaStream_t s = as_stream(stream);
+  const unsigned tiles = (unsigned)ceil_div64(npix, TORGB_TILE);
   if (cin >= 128) {
-    torgb_kernel<32><<<grid_for(npix, 256 / 32), 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
+    torgb_kernel<32><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
                                                               pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
   } else if (cin >= 32) {
-    torgb_kernel<8><<<grid_for(npix, 256 / 8), 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
+    torgb_kernel<8><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
                                                             pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
   } else {
-    torgb_kernel<4><<<grid_for(npix, 256 / 4), 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
+    torgb_kernel<4><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
                                                             pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
   }
   return check_launch("torgb");

@@ -113,6 +113,27 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
+// one elected lane of a fully converged warp (PTX elect.sync); keeps the surrounding control flow warp-uniform so the
+// compiler emits single UTCHMMA / UBLKCP instructions instead of a per-active-lane issue loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// streaming activation load: read-only path, do not allocate in L1 (the tiny L1 left beside ~200 KB of shared memory
+// must keep the per-channel epilogue vectors and style rows resident)
+__device__ __forceinline__ float4 ldg_stream4(const float4* ptr) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x (low 16 bits) = lo_elem
   return *reinterpret_cast<uint32_t*>(&v);

@@ -222,7 +222,7 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
 
 def linear_rows(x_ptr_tensor: torch.Tensor, rows: int, row_stride: int, offset: int, pw: PackedConv, bias=None,
                 act=L.ACT_NONE, slope=0.0, gain=1.0, in_square=False, out: Optional[torch.Tensor] = None,
-                engine: Optional[str] = None) -> torch.Tensor:
+                engine: Optional[str] = None, launch: bool = True):
     """y[r,:] = act(W x[r,:] + bias) for `rows` vectors of length pw.cin starting at element `offset`
     of `x_ptr_tensor`, consecutive rows `row_stride` elements apart (all in floats)."""
     dev = x_ptr_tensor.device
@@ -242,6 +242,8 @@ def linear_rows(x_ptr_tensor: torch.Tensor, rows: int, row_stride: int, offset: 
         p.ch_shift = bias.data_ptr()
     p.act, p.act_slope, p.act_gain = act, slope, gain
     p.out, p.out_pitch = out.data_ptr(), out.stride(0)
+    if not launch:                      # caller batches several problems into one launch (L.conv_batched)
+        return out, p
     eng = engine or "f32"
     L.conv(p, pw.tc if (eng == "tc" and pw.tc is not None) else None)
     return out

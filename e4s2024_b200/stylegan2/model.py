@@ -187,12 +187,13 @@ class ModulatedConv2d(nn.Module):
             d = E.linear_rows(s, st.rows, self.in_channel, 0, wsq, act=L.ACT_RSQRT_EPS, slope=self.eps, in_square=True)
         return s, d
 
-    def run(self, x: View, st: StyleRows, ctx: Optional[E.RegionCtx], **epilogue) -> View:
-        """Fused modulated convolution on an NHWC view; `epilogue` = noise/bias/activation kwargs of engine.conv."""
+    def run(self, x: View, st: StyleRows, ctx: Optional[E.RegionCtx], tables=None, **epilogue) -> View:
+        """Fused modulated convolution on an NHWC view; `epilogue` = noise/bias/activation kwargs of engine.conv.
+        `tables` = precomputed (s, d) (Generator.forward batches all layers' table GEMMs into two launches)."""
         if self.downsample:
             raise NotImplementedError("downsample=True is only used by the (training-only) Discriminator")
         conv, _ = self.packed()
-        s, d = self.tables(st)
+        s, d = tables if tables is not None else self.tables(st)
         regional = st.regions > 1
         if regional and ctx is None:
             raise L.E4SError("regional styles need a mask")
@@ -264,12 +265,12 @@ class StyledConv(nn.Module):
         self.activate = FusedLeakyReLU(out_channel)
         self.mask_op = mask_op
 
-    def run(self, x: View, st: StyleRows, ctx, noise) -> View:
+    def run(self, x: View, st: StyleRows, ctx, noise, tables=None) -> View:
         b, h, w = x.bhw
         if self.conv.upsample:
             h, w = 2 * h, 2 * w
         nz = _noise_for(noise, b, h, w, x.t.device)
-        return self.conv.run(x, st, ctx if self.mask_op else None, noise=nz, noise_w=self.noise.weight.detach(),
+        return self.conv.run(x, st, ctx if self.mask_op else None, tables=tables, noise=nz, noise_w=self.noise.weight.detach(),
                              ch_shift=self.activate.bias.detach(), act=L.ACT_LRELU,
                              slope=self.activate.negative_slope, gain=self.activate.scale)
 
@@ -298,10 +299,10 @@ class ToRGB(nn.Module):
             self._wrgb = (key, w)
         return self._wrgb[1]
 
-    def run(self, x: View, st: StyleRows, ctx, skip: Optional[torch.Tensor]) -> torch.Tensor:
+    def run(self, x: View, st: StyleRows, ctx, skip: Optional[torch.Tensor], tables=None) -> torch.Tensor:
         """x NHWC view, skip NCHW [B,3,H/2,W/2] or None -> rgb NCHW [B,3,H,W]."""
         b, h, w = x.bhw
-        s = self.conv.modulation.rows(st.t, st.rows, st.stride, st.offset)
+        s = tables[0] if tables is not None else self.conv.modulation.rows(st.t, st.rows, st.stride, st.offset)
         rgb = torch.empty(b, 3, h, w, device=x.t.device, dtype=torch.float32)
         fir = None
         if skip is not None:
@@ -417,32 +418,69 @@ class Generator(nn.Module):
         def glob(i):          # latent[:, 0, i]
             return StyleRows(latent, b, k * nl * sd, i * sd, 1)
 
-        x = View(L.nchw_to_nhwc(self.input.input.detach().float().repeat(b, 1, 1, 1).contiguous()))
-        out = self.conv1.run(x, regional(0), ctx, noise[0])
-        skip = self.to_rgb1.run(out, regional(1), ctx, None)
-        intermediate_feats = None
+        # which style rows feed which layer (model.py:661-690), then ALL style tables in two batched launches
         rl = self.remaining_layer_idx
+        plan = [(self.conv1.conv, regional(0)), (self.to_rgb1.conv, regional(1))]
+        i = 1
+        for conv1, conv2, to_rgb in zip(self.convs[::2], self.convs[1::2], self.to_rgbs):
+            if i < rl:
+                st3 = regional(i + 2) if (rl == 17 or i + 2 != rl) else glob(i + 2)
+                plan += [(conv1.conv, regional(i)), (conv2.conv, regional(i + 1)), (to_rgb.conv, st3)]
+            else:
+                plan += [(conv1.conv, glob(i)), (conv2.conv, glob(i + 1)), (to_rgb.conv, glob(i + 2))]
+            i += 2
+        tabs = _batched_tables(plan)
+        sty = {id(mc): st for mc, st in plan}
+
+        def sconv(layer, xin, nz):
+            return layer.run(xin, sty[id(layer.conv)], ctx, nz, tables=tabs[id(layer.conv)])
+
+        def rgb(layer, xin, skip_):
+            return layer.run(xin, sty[id(layer.conv)], ctx, skip_, tables=tabs[id(layer.conv)])
+
+        x = View(L.nchw_to_nhwc(self.input.input.detach().float().repeat(b, 1, 1, 1).contiguous()))
+        out = sconv(self.conv1, x, noise[0])
+        skip = rgb(self.to_rgb1, out, None)
+        intermediate_feats = None
         i = 1
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
                                                         self.to_rgbs):
-            if i < rl:
-                out = conv1.run(out, regional(i), ctx, noise1)
-                if i + 2 == self.split_layer_idx:
-                    if use_structure_code:
-                        out = View(L.nchw_to_nhwc(structure_feats.contiguous().float()))
-                    intermediate_feats = L.nhwc_to_nchw(out.t)
-                out = conv2.run(out, regional(i + 1), ctx, noise2)
-                st = regional(i + 2) if (rl == 17 or i + 2 != rl) else glob(i + 2)
-                skip = to_rgb.run(out, st, ctx, skip)
-            else:
-                out = conv1.run(out, glob(i), ctx, noise1)
-                out = conv2.run(out, glob(i + 1), ctx, noise2)
-                skip = to_rgb.run(out, glob(i + 2), ctx, skip)
+            out = sconv(conv1, out, noise1)
+            if i < rl and i + 2 == self.split_layer_idx:
+                if use_structure_code:
+                    out = View(L.nchw_to_nhwc(structure_feats.contiguous().float()))
+                intermediate_feats = L.nhwc_to_nchw(out.t)
+            out = sconv(conv2, out, noise2)
+            skip = rgb(to_rgb, out, skip)
             i += 2
         image = skip
         if return_latents:
             return image, latent, intermediate_feats
         return image, None, intermediate_feats
+
+
+def _batched_tables(plan):
+    """plan: [(ModulatedConv2d, StyleRows)] -> {id(module): (s, d)} with all modulation GEMMs in one batched launch
+    and all demodulation GEMMs in a second one (they were 43 tiny launches per forward)."""
+    ps, ss = [], []
+    for mc, st in plan:
+        pw, bias = mc.modulation.packed()
+        s_, p_ = E.linear_rows(st.t, st.rows, st.stride, st.offset, pw, bias=bias, launch=False)
+        ps.append(p_)
+        ss.append(s_)
+    L.conv_batched(ps)
+    pd, tabs = [], {}
+    for (mc, st), s_ in zip(plan, ss):
+        d_ = None
+        if mc.demodulate:
+            _, wsq = mc.packed()
+            d_, p_ = E.linear_rows(s_, st.rows, mc.in_channel, 0, wsq, act=L.ACT_RSQRT_EPS, slope=mc.eps, in_square=True,
+                                   launch=False)
+            pd.append(p_)
+        tabs[id(mc)] = (s_, d_)
+    if pd:
+        L.conv_batched(pd)
+    return tabs
 
 
 def generator_state_shapes(size: int, style_dim: int = 512, n_mlp: int = 8, **kw):

@@ -106,6 +106,8 @@ int e4s_sizeof_conv(void);
 
 /* fp32 CUDA-core implicit GEMM.  w layout: [phase][K][cout_pad] (phase = 1 or 4). */
 int e4s_conv_f32(const E4SConv* p, void* stream);
+/* `count` independent E4S_CONV_NORMAL problems (host array) in one launch per 32 problems: blockIdx.z = problem */
+int e4s_conv_f32_batched(const E4SConv* params, int count, void* stream);
 
 /* tcgen05 (5th-gen tensor core) implicit GEMM with the 3-pass bf16 hi/lo split (fp32 accumulate in TMEM).
  * w points to the packed bf16 image produced by e4s_pack_weights_tc; cin % 8 == 0, cout in {32,64,128,256*n}. */
@@ -113,6 +115,8 @@ int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream);
 /* bytes needed for the packed tensor-core weights of a [phases, K, cout] fp32 matrix */
 int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);
 /* w_f32: [phases][K][cout_pad] (the e4s_conv_f32 layout) -> w_packed (hi/lo bf16, UMMA K-major SW128 tiles) */
+/* debug aid: record a (role, job, event, clock64) timeline of CTA 0 of the halo kernel into buf (2 x u64 per record); NULL removes it */
+int e4s_debug_halo_trace(void* buf, int cap_records);
 int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cout, int cout_pad, void* w_packed, void* stream);
 
 /* upfirdn2d on NCHW fp32 [planes, in_h, in_w] (planes = B*C). kernel [kh,kw] is correlated FLIPPED. */

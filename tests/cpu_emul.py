@@ -131,6 +131,11 @@ def conv(p: L.E4SConv, tc_weights=None):
             out[oidx] = acc
 
 
+def conv_batched(params_list):
+    for p in params_list:
+        conv(p)
+
+
 def pack_weights_tc(w, phases, k, cout, cout_pad):
     return None
 
@@ -291,7 +296,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
     return nchw_to_nhwc(y, c_pad)
 
 
-_NAMES = ["conv", "pack_weights_tc", "upfirdn2d", "bias_act", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
+_NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "bias_act", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
           "mask_labels", "labels_to_onehot", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
