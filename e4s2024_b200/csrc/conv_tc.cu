@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
           iy >>= p.in_shift;
           ix >>= p.in_shift;
           const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)rb[i] * p.hin + iy) * p.win + ix) * p.x_pitch + ci);
-          v[i][0] = ldg_stream4(src);
-          v[i][1] = ldg_stream4(src + 1);
+          v[i][0] = __ldg(src);          // allocate in L1: the 9 taps re-read these lines
+          v[i][1] = __ldg(src + 1);
         }
       }
     };

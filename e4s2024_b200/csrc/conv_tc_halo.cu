@@ -25,7 +25,8 @@ namespace e4s {
 constexpr int HL_TH = 16, HL_TW = 8;
 constexpr int HL_HP = HL_TW + 2;                  // halo row pitch (pixels)
 constexpr int HL_HPIX = (HL_TH + 2) * HL_HP;      // 180 halo pixels
-constexpr int HL_PLANE = 23 * 1024;               // one bf16 plane (hi or lo): 180 * 128 B rounded up to 1 KB
+constexpr int HL_PLANE = HL_HPIX * 128;            // one bf16 plane (hi or lo): 180 pixel rows of 128 B (NOT 1 KB aligned:
+                                                  // the swizzle phase is taken from the absolute shared-memory address)
 constexpr int HL_HALO_STAGES = 2;
 constexpr int HL_THREADS = 14 * 32;
 constexpr int HL_MMA_WARP = 12;             // warps 8-11 epilogue, 12 MMA issuer, 13 weight loader
@@ -33,7 +34,7 @@ constexpr int HL_ITEMS = (HL_HPIX + 31) / 32;     // 6 (pixel, 8-channel) items 
 
 __host__ __device__ constexpr int hl_b_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 4 : 6); }
 __host__ __device__ constexpr int hl_smem_bytes(int bn) {
-  return HL_HALO_STAGES * 2 * HL_PLANE + hl_b_stages(bn) * 2 * bn * 128 + 512 + 1024;
+  return HL_HALO_STAGES * 2 * HL_PLANE + hl_b_stages(bn) * 2 * bn * 128 + 2 * 3 * bn * 4 + 512 + 1024;
 }
 
 __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
@@ -71,7 +72,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   // [halo stage 0: hi | lo][halo stage 1: hi | lo][B ring: BST x (hi | lo)][barriers]
   constexpr int HALO_BYTES = 2 * HL_PLANE;
   constexpr int B_OFF = HL_HALO_STAGES * HALO_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * 2 * B_BYTES);
+  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * 2 * B_BYTES);        // [2 slots][mul | add | prelu][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * 2 * B_BYTES + 2 * 3 * BN * 4);
   const uint32_t bar_hfull = smem_u32(bars);                 // 2
   const uint32_t bar_hempty = bar_hfull + 16;                // 2
   const uint32_t bar_bfull = bar_hempty + 16;                // BST
@@ -201,9 +203,12 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
             hi[j] = h;
             lo[j] = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
           }
-          const uint32_t off = px * 128 + ((cg ^ (px & 7)) << 4);       // swizzle on the absolute 128B-row index
+          // 128B swizzle on ABSOLUTE shared-memory address bits [7:9] (the plane base is only 128-byte aligned)
+          const uint32_t rowaddr = (uint32_t)(hs * HALO_BYTES) + px * 128;
+          const uint32_t off = px * 128 + ((cg ^ ((rowaddr >> 7) & 7)) << 4);
+          const uint32_t off_lo = px * 128 + ((cg ^ (((rowaddr + HL_PLANE) >> 7) & 7)) << 4);
           *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(h_lo + off_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       if (tid == 0) hl_trace(0, hg, 2);
@@ -243,6 +248,17 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         er[ph].nz = (er[ph].nrow && p.noise_sc == 0) ? nw * __ldg(er[ph].nrow) : 0.f;
       }
       if (warp == 8 && lane == 0) hl_trace(1, it, 0);
+      // fused per-channel vectors of this job -> shared memory (demod is per sample; everything else per layer)
+      float* sv = s_epi + (it & 1) * 3 * BN;
+      for (int n = tid - 8 * 32; n < BN; n += 128) {
+        const int ng = jb.nt * BN + n;
+        float mul = drow ? __ldg(drow + ng) : 1.f;
+        if (p.ch_scale) mul *= __ldg(p.ch_scale + ng);
+        sv[n] = mul;
+        sv[BN + n] = p.ch_shift ? __ldg(p.ch_shift + ng) : 0.f;
+        sv[2 * BN + n] = p.act == E4S_ACT_PRELU ? __ldg(p.act_prelu + ng) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
       mbar_wait(bar_afull + 8 * set, use & 1);
       tc_fence_after();
       if (warp == 8 && lane == 0) hl_trace(1, it, 1);
@@ -254,7 +270,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float acc[16];
           tmem_ld16(tacc + (uint32_t)c0, acc);
-          tc_epilogue16(p, acc, jb.nt * BN + c0, er[ph]);
+          tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph]);
         }
       }
       tc_fence_before();

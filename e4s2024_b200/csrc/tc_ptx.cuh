@@ -166,60 +166,87 @@ __device__ __forceinline__ float tc_act(float t, int act, float slope, float gai
   }
 }
 
+// One float4 group of the epilogue given the (already fetched) per-channel vectors.
+__device__ __forceinline__ float4 tc_epi_math4(const E4SConv& p, float4 a, const TcEpiRow& r, const int n, const float4 mul, const float4 add,
+                                               const float4 prelu) {
+  a.x *= mul.x; a.y *= mul.y; a.z *= mul.z; a.w *= mul.w;          // demod * channel scale
+  if (p.pixw) {
+    a.x *= r.pw; a.y *= r.pw; a.z *= r.pw; a.w *= r.pw;
+  }
+  if (r.nrow) {
+    if (p.noise_sc == 0) {
+      a.x += r.nz; a.y += r.nz; a.z += r.nz; a.w += r.nz;
+    } else {
+      a.x += r.nw * __ldg(r.nrow + (int64_t)n * p.noise_sc);
+      a.y += r.nw * __ldg(r.nrow + (int64_t)(n + 1) * p.noise_sc);
+      a.z += r.nw * __ldg(r.nrow + (int64_t)(n + 2) * p.noise_sc);
+      a.w += r.nw * __ldg(r.nrow + (int64_t)(n + 3) * p.noise_sc);
+    }
+  }
+  a.x += add.x; a.y += add.y; a.z += add.z; a.w += add.w;          // bias / BN shift
+  float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.res) {
+    rs = ldg4(p.res + r.pix * p.res_pitch + n);
+    if (!p.res_after_act) {
+      a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
+    }
+  }
+  if (p.act == E4S_ACT_PRELU) {
+    a.x = a.x < 0.f ? a.x * prelu.x : a.x; a.y = a.y < 0.f ? a.y * prelu.y : a.y;
+    a.z = a.z < 0.f ? a.z * prelu.z : a.z; a.w = a.w < 0.f ? a.w * prelu.w : a.w;
+  } else if (p.act != E4S_ACT_NONE) {
+    a.x = tc_act(a.x, p.act, p.act_slope, p.act_gain); a.y = tc_act(a.y, p.act, p.act_slope, p.act_gain);
+    a.z = tc_act(a.z, p.act, p.act_slope, p.act_gain); a.w = tc_act(a.w, p.act, p.act_slope, p.act_gain);
+  }
+  if (p.res && p.res_after_act) {
+    a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
+  }
+  return a;
+}
+
+__device__ __forceinline__ void tc_epi_store4(const E4SConv& p, float4* o, float4 a) {
+  if (p.accumulate) {
+    const float4 old = *o;
+    a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
+  }
+  *o = a;
+}
+
+// per-channel vectors from global memory (per-row demodulation: gather kernel).  All loads are issued before the
+// first use so their L2 latency overlaps (they were serialised per float4 group in the first version).
 __device__ __forceinline__ void tc_epilogue16(const E4SConv& p, const float (&acc)[16], const int n0, const TcEpiRow& r) {
-  float4* o = reinterpret_cast<float4*>(p.out + r.pix * p.out_pitch + n0);
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 mul[4], add[4], pre[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int n = n0 + 4 * q;
-    float4 a = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    if (r.drow) {
-      const float4 d = ldg4(r.drow + n);
-      a.x *= d.x; a.y *= d.y; a.z *= d.z; a.w *= d.w;
-    }
-    if (p.pixw) {
-      a.x *= r.pw; a.y *= r.pw; a.z *= r.pw; a.w *= r.pw;
-    }
+    mul[q] = r.drow ? ldg4(r.drow + n) : one;
     if (p.ch_scale) {
       const float4 s = ldg4(p.ch_scale + n);
-      a.x *= s.x; a.y *= s.y; a.z *= s.z; a.w *= s.w;
+      mul[q].x *= s.x; mul[q].y *= s.y; mul[q].z *= s.z; mul[q].w *= s.w;
     }
-    if (r.nrow) {
-      if (p.noise_sc == 0) {
-        a.x += r.nz; a.y += r.nz; a.z += r.nz; a.w += r.nz;
-      } else {
-        a.x += r.nw * __ldg(r.nrow + (int64_t)n * p.noise_sc);
-        a.y += r.nw * __ldg(r.nrow + (int64_t)(n + 1) * p.noise_sc);
-        a.z += r.nw * __ldg(r.nrow + (int64_t)(n + 2) * p.noise_sc);
-        a.w += r.nw * __ldg(r.nrow + (int64_t)(n + 3) * p.noise_sc);
-      }
-    }
-    if (p.ch_shift) {
-      const float4 s = ldg4(p.ch_shift + n);
-      a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
-    }
-    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.res) {
-      rs = ldg4(p.res + r.pix * p.res_pitch + n);
-      if (!p.res_after_act) {
-        a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
-      }
-    }
-    if (p.act == E4S_ACT_PRELU) {
-      const float4 s = ldg4(p.act_prelu + n);
-      a.x = a.x < 0.f ? a.x * s.x : a.x; a.y = a.y < 0.f ? a.y * s.y : a.y;
-      a.z = a.z < 0.f ? a.z * s.z : a.z; a.w = a.w < 0.f ? a.w * s.w : a.w;
-    } else if (p.act != E4S_ACT_NONE) {
-      a.x = tc_act(a.x, p.act, p.act_slope, p.act_gain); a.y = tc_act(a.y, p.act, p.act_slope, p.act_gain);
-      a.z = tc_act(a.z, p.act, p.act_slope, p.act_gain); a.w = tc_act(a.w, p.act, p.act_slope, p.act_gain);
-    }
-    if (p.res && p.res_after_act) {
-      a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
-    }
-    if (p.accumulate) {
-      const float4 old = o[q];
-      a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
-    }
-    o[q] = a;
+    add[q] = p.ch_shift ? ldg4(p.ch_shift + n) : zero;
+    pre[q] = p.act == E4S_ACT_PRELU ? ldg4(p.act_prelu + n) : zero;
+  }
+  float4* o = reinterpret_cast<float4*>(p.out + r.pix * p.out_pitch + n0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    tc_epi_store4(p, o + q, tc_epi_math4(p, a, r, n0 + 4 * q, mul[q], add[q], pre[q]));
+  }
+}
+
+// per-channel vectors staged in shared memory by the caller: sv = [mul(BN) | add(BN) | prelu(BN)], nl = local channel
+__device__ __forceinline__ void tc_epilogue16_sv(const E4SConv& p, const float (&acc)[16], const int n0, const int nl, const int bn,
+                                                 const float* sv, const TcEpiRow& r) {
+  float4* o = reinterpret_cast<float4*>(p.out + r.pix * p.out_pitch + n0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 mul = *reinterpret_cast<const float4*>(sv + nl + 4 * q);
+    const float4 add = *reinterpret_cast<const float4*>(sv + bn + nl + 4 * q);
+    const float4 pre = *reinterpret_cast<const float4*>(sv + 2 * bn + nl + 4 * q);
+    const float4 a = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    tc_epi_store4(p, o + q, tc_epi_math4(p, a, r, n0 + 4 * q, mul, add, pre));
   }
 }
 
