@@ -46,7 +46,7 @@ class E4SConv(C.Structure):
 
 EXPORTS = [
     "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc",
-    "e4s_debug_halo_trace", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
@@ -122,12 +122,12 @@ def conv_batched(params_list):
     _check(lib().e4s_conv_f32_batched(arr, n, _stream()), "e4s_conv_f32_batched")
 
 
-def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cout: int, cout_pad: int) -> torch.Tensor:
+def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cin: int, cout: int, cout_pad: int) -> torch.Tensor:
     nbytes = int(lib().e4s_pack_weights_tc_bytes(phases, k, cout))
     if nbytes <= 0:
         raise E4SError("e4s_pack_weights_tc_bytes: unsupported shape")
     out = torch.empty(nbytes, dtype=torch.uint8, device=w_f32.device)
-    _check(lib().e4s_pack_weights_tc(C.c_void_p(w_f32.data_ptr()), phases, k, cout, cout_pad, C.c_void_p(out.data_ptr()),
+    _check(lib().e4s_pack_weights_tc(C.c_void_p(w_f32.data_ptr()), phases, k, cin, cout, cout_pad, C.c_void_p(out.data_ptr()),
                                      _stream()), "e4s_pack_weights_tc")
     return out
 

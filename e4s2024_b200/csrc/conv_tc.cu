@@ -30,7 +30,8 @@ struct TcRow {
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int64_t m_total) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int64_t m_total,
+                                                                  const int tile2d) {
   constexpr int STAGES = tc_stages(BN);
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BN);
@@ -58,7 +59,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   if (tid < TC_BM) {
     int64_t m = (int64_t)blockIdx.x * TC_BM + tid;
     TcRow rw{-1, 0, 0, 0};
-    if (m < m_total) {
+    if (tile2d) {
+      // 16 x 8 pixel tiles: the 3x3 halo of a tile is 18 x 10 pixels instead of 3 x 130 for a 1 x 128 row segment, so the
+      // 9 taps of one 64-channel chunk (46 KB) are re-read from L1 instead of L2
+      const int gw = up ? p.win : p.wout, gh = up ? p.hin : p.hout;
+      const int tx_n = gw >> 3, ty_n = gh >> 4;
+      int t = (int)blockIdx.x;
+      const int txi = t % tx_n;
+      t /= tx_n;
+      const int tyi = t % ty_n;
+      rw.b = t / ty_n;
+      const int yy = tyi * 16 + (tid >> 3), xx = txi * 8 + (tid & 7);
+      rw.oy = up ? 2 * yy + py : yy;
+      rw.ox = up ? 2 * xx + px : xx;
+      if (p.labels) {
+        int sy = nearest_src(rw.oy, p.lab_h, p.hout), sx = nearest_src(rw.ox, p.lab_w, p.wout);
+        rw.r = p.labels[((int64_t)rw.b * p.lab_h + sy) * p.lab_w + sx];
+      }
+    } else if (m < m_total) {
       if (up) {
         int hw = p.hin * p.win;
         rw.b = (int)(m / hw);
@@ -121,15 +139,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     }
     const int hv = p.hin << p.in_shift, wv = p.win << p.in_shift;
     const int kwid = up ? 3 : p.kw;
+    const int ntaps = p.kh * p.kw;
+    const bool grouped = (p.cin % 64) == 0;
 
     float4 v[4][2];
     bool ok[4];
     auto prefetch = [&](int kc) {
-      const int k0 = kc * TC_BK + cg * 8;            // this thread's 8 consecutive k (one tap: cin % 8 == 0)
-      const int tap = k0 / p.cin;
-      const int ci = k0 - tap * p.cin;
+      // K order of the packed weights (tc_chunk_k): 64-channel group outer, tap inner when cin % 64 == 0, so the taps of
+      // one channel group run back to back over the same (L1-resident) input window; plain k = tap*cin + ci otherwise
+      int tap, ci;
+      bool tap_ok;
+      if (grouped) {
+        const int g = kc / ntaps;
+        tap = kc - g * ntaps;
+        ci = g * 64 + cg * 8;
+        tap_ok = true;
+      } else {
+        const int k0 = kc * TC_BK + cg * 8;
+        tap = k0 / p.cin;
+        ci = k0 - tap * p.cin;
+        tap_ok = k0 < K;
+      }
       const int ky = tap / kwid, kx = tap - ky * kwid;
-      const bool tap_ok = k0 < K;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         int iy = ry[i] + ky, ix = rx[i] + kx;
@@ -151,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       mbar_wait(bar_empty + 8 * s, par ^ 1);
       uint8_t* a_hi = smem + s * STAGE_BYTES;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
-      const int ci = (kc * TC_BK + cg * 8) % p.cin;
+      const int ci = grouped ? (kc / ntaps) * 64 + cg * 8 : (kc * TC_BK + cg * 8) % p.cin;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = r0 + 32 * i;
@@ -274,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
 
 // w_f32 [phases][K][cout_pad] -> per (phase, n_tile, k_chunk): B_hi tile | B_lo tile, each BN rows x 128 bytes,
 // row n holds k = chunk*64 .. +63 (bf16) with the 16-byte chunks XOR-swizzled by (n % 8)  == the smem image.
-__global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int cout, int cout_pad, int bn, uint8_t* __restrict__ out,
+__global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int cin, int cout, int cout_pad, int bn, uint8_t* __restrict__ out,
                                        int64_t total) {
   const int num_kc = (K + TC_BK - 1) / TC_BK, nt = cout / bn;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -287,7 +318,15 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int c
     t /= num_kc;
     int ntile = (int)(t % nt);
     int ph = (int)(t / nt);
-    const int k = kc * TC_BK + kp * 2, n = ntile * bn + nl;
+    // chunk -> k: group-major when cin % 64 == 0 (see conv_tc_kernel), linear otherwise
+    const int n = ntile * bn + nl;
+    int k;
+    if (cin % 64 == 0) {
+      const int ntaps = K / cin, g = kc / ntaps, tap = kc - g * ntaps;
+      k = tap * cin + g * 64 + kp * 2;
+    } else {
+      k = kc * TC_BK + kp * 2;
+    }
     const float a = k < K ? w[((int64_t)ph * K + k) * cout_pad + n] : 0.f;
     const float b = k + 1 < K ? w[((int64_t)ph * K + k + 1) * cout_pad + n] : 0.f;
     const uint32_t h = pack_bf16x2(a, b);
@@ -322,7 +361,9 @@ static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStr
   }
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   dim3 grid((unsigned)ceil_div64(m_total, TC_BM), (unsigned)(p->cout / BN), up ? 4 : 1);
-  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total);
+  const int gw = up ? p->win : p->wout, gh = up ? p->hin : p->hout;
+  const int tile2d = (gw % 8 == 0 && gh % 16 == 0) ? 1 : 0;       // full 16x8 tiles only (tile count is the same)
+  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, tile2d);
   return check_launch("e4s_conv_tc");
 }
 
@@ -335,15 +376,16 @@ extern "C" int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout) {
   return (int64_t)phases * ((k + TC_BK - 1) / TC_BK * TC_BK) * cout * 4;  // hi + lo bf16 per (zero-padded) weight
 }
 
-extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cout, int cout_pad, void* w_packed, void* stream) {
+extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, void* w_packed, void* stream) {
   E4S_REQUIRE(w_f32 && w_packed, "pack_weights_tc: null pointer");
   E4S_REQUIRE(phases >= 1 && tc_shape_ok(k, cout) && cout_pad >= cout, "pack_weights_tc: unsupported shape K=%d cout=%d", k, cout);
+  E4S_REQUIRE(cin >= 8 && cin % 8 == 0 && k % cin == 0, "pack_weights_tc: K=%d must be taps * cin (cin=%d)", k, cin);
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "pack_weights_tc: output must be 16-byte aligned");
   const int bn = tc_block_n(cout);
   const int64_t total = (int64_t)phases * (cout / bn) * ((k + TC_BK - 1) / TC_BK) * bn * 32;
   int64_t g = ceil_div64(total, 256);
   if (g > 148 * 32) g = 148 * 32;
-  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, k, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
+  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, k, cin, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
   return check_launch("pack_weights_tc");
 }
 

@@ -49,6 +49,7 @@ struct HlJob {
 __device__ unsigned long long* g_hl_trace = nullptr;
 __device__ int g_hl_trace_cap = 0;
 __device__ int g_hl_trace_n = 0;
+__device__ int g_hl_dbg = 0;      // profiling experiments: bit0 skip epilogue math+stores, bit1 skip tcgen05.ld, bit2 skip MMAs
 __device__ __forceinline__ void hl_trace(int role, int it, int ev) {
   if (g_hl_trace == nullptr || blockIdx.x != 0) return;
   const int i = atomicAdd(&g_hl_trace_n, 1);
@@ -224,6 +225,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     const int row = q * 32 + lane;                           // GEMM row = ty*8 + tx
     const int ty = row >> 3, tx = row & 7;
     const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    const int dbg = g_hl_dbg;
     for (int it = 0; it < my_jobs; ++it) {
       const HlJob jb = decode(it);
       const int set = nsets == 2 ? (it & 1) : 0;
@@ -269,8 +271,13 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float acc[16];
-          tmem_ld16(tacc + (uint32_t)c0, acc);
-          tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph]);
+          if (!(dbg & 2)) {
+            tmem_ld16(tacc + (uint32_t)c0, acc);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+          }
+          if (!(dbg & 1)) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph]);
         }
       }
       tc_fence_before();
@@ -307,7 +314,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
                 if (tap >= 9) break;
                 const uint32_t aoff = (uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u;
                 const uint32_t boff = (uint32_t)(tt * cin_eff * 2);
-                if (elect_one()) {
+                if (!(g_hl_dbg & 4) && elect_one()) {
                   for (int k = 0; k < ksteps; ++k) {
                     const uint64_t dah = umma_smem_desc_sbo(h_hi + aoff + k * 32, HL_HP * 128);
                     const uint64_t dal = umma_smem_desc_sbo(h_lo + aoff + k * 32, HL_HP * 128);
@@ -344,7 +351,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
             const uint8_t* src = wpk + ((int64_t)ph * n_tiles + jb.nt) * num_kc * tile_bytes;
             for (int c = 0; c < CPG; ++c, ++bc) {
               const int bs = bc % BST;
-              const int kc = tpc == 1 ? c * G + g : c;       // packed chunk = k / 64 with k = tap*cin + ci
+              const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
               mbar_wait(bar_bempty + 8 * bs, ((bc / BST) & 1) ^ 1);
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * B_BYTES);
@@ -403,6 +410,11 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
   return check_launch("e4s_conv_tc(halo)");
 }
 
+int tc_halo_set_flags(int flags) {
+  cudaError_t e = cudaMemcpyToSymbol(g_hl_dbg, &flags, sizeof(int));
+  return e == cudaSuccess ? E4S_OK : fail(E4S_ERR_CUDA, "halo flags: %s", cudaGetErrorString(e));
+}
+
 int tc_halo_set_trace(void* buf, int cap_records) {
   unsigned long long* ptr = static_cast<unsigned long long*>(buf);
   int zero = 0;
@@ -426,3 +438,4 @@ int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
 
 // debug aid (not part of the reference-facing surface): install / remove a clock64 timeline buffer for CTA 0 of the halo kernel
 extern "C" int e4s_debug_halo_trace(void* buf, int cap_records) { return e4s::tc_halo_set_trace(buf, cap_records); }
+extern "C" int e4s_debug_halo_flags(int flags) { return e4s::tc_halo_set_flags(flags); }

@@ -69,7 +69,7 @@ def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, pha
     w_pkc = w_pkc.contiguous().float()
     pc = PackedConv(w_pkc, cin, cout, cout_pad, kh, kw, phases)
     if want_tc and w_pkc.is_cuda and tc_eligible(cin, cout) and tc_available():
-        pc.tc = L.pack_weights_tc(w_pkc, phases, pc.k, cout, cout_pad)
+        pc.tc = L.pack_weights_tc(w_pkc, phases, pc.k, cin, cout, cout_pad)
     return pc
 
 

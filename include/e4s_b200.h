@@ -114,10 +114,13 @@ int e4s_conv_f32_batched(const E4SConv* params, int count, void* stream);
 int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream);
 /* bytes needed for the packed tensor-core weights of a [phases, K, cout] fp32 matrix */
 int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);
-/* w_f32: [phases][K][cout_pad] (the e4s_conv_f32 layout) -> w_packed (hi/lo bf16, UMMA K-major SW128 tiles) */
+/* w_f32: [phases][K = taps*cin][cout_pad] (the e4s_conv_f32 layout) -> w_packed (hi/lo bf16, UMMA K-major SW128 tiles;
+ * 64-wide K chunks ordered channel-group-major when cin % 64 == 0) */
 /* debug aid: record a (role, job, event, clock64) timeline of CTA 0 of the halo kernel into buf (2 x u64 per record); NULL removes it */
 int e4s_debug_halo_trace(void* buf, int cap_records);
-int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cout, int cout_pad, void* w_packed, void* stream);
+/* debug aid: profiling experiments on the halo kernel (bit0 skip epilogue math+stores, bit1 skip tcgen05.ld, bit2 skip MMAs); 0 = normal */
+int e4s_debug_halo_flags(int flags);
+int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, void* w_packed, void* stream);
 
 /* upfirdn2d on NCHW fp32 [planes, in_h, in_w] (planes = B*C). kernel [kh,kw] is correlated FLIPPED. */
 int e4s_upfirdn2d_f32(const float* x, const float* kernel, float* out, int64_t planes, int in_h, int in_w,
