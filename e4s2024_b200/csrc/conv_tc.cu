@@ -215,10 +215,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      if (kc + 1 < num_kc) prefetch(kc + 1);
+      // publish the stage BEFORE issuing the next chunk's global loads: fence.proxy.async waits for the thread's
+      // outstanding memory operations, so a prefetch issued ahead of it is not a prefetch at all
       fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (kc + 1 < num_kc) prefetch(kc + 1);
     }
 
     // =========================== epilogue ========================================================

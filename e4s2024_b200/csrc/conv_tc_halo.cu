@@ -213,10 +213,12 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         }
       }
       if (tid == 0) hl_trace(0, hg, 2);
-      prefetch(hg + 1);
+      // publish the halo FIRST: fence.proxy.async waits for this thread's outstanding memory operations, so issuing the
+      // next job's global loads before it would serialise their full DRAM latency into every job
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
+      prefetch(hg + 1);
       if (tid == 0) hl_trace(0, hg, 3);
     }
   } else if (warp < HL_MMA_WARP) {
