@@ -17,15 +17,17 @@ struct Row {
   int b, oy, ox, r;
 };
 
+// no `switch` / long if-chain on `act`: nvcc lowers those to a per-element jump table (LDC + BRX), very slow here
 __device__ __forceinline__ float apply_act(float v, int act, float slope, float gain, const float* prelu, int n) {
-  switch (act) {
-    case E4S_ACT_LRELU: return (v < 0.f ? v * slope : v) * gain;
-    case E4S_ACT_RELU: return fmaxf(v, 0.f);
-    case E4S_ACT_PRELU: return v < 0.f ? v * __ldg(prelu + n) : v;
-    case E4S_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    case E4S_ACT_RSQRT_EPS: return rsqrtf(v + slope);
-    default: return v;
+  if (act <= E4S_ACT_RELU) {   // NONE / LRELU / RELU: (v < 0 ? v*sl : v) * g (+ lower clamp at 0 for RELU)
+    const float sl = act == E4S_ACT_LRELU ? slope : 1.f;
+    const float g = act == E4S_ACT_LRELU ? gain : 1.f;
+    const float lo = act == E4S_ACT_RELU ? 0.f : -INFINITY;
+    return fmaxf((v < 0.f ? v * sl : v) * g, lo);
   }
+  if (act == E4S_ACT_PRELU) return v < 0.f ? v * __ldg(prelu + n) : v;
+  if (act == E4S_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return rsqrtf(v + slope);   // E4S_ACT_RSQRT_EPS
 }
 
 template <int BN>

@@ -279,7 +279,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.f;
           }
-          if (!(dbg & 1)) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph]);
+          if (!(dbg & 1)) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph], dbg);
         }
       }
       tc_fence_before();

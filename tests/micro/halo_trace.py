@@ -21,7 +21,7 @@ nw = torch.tensor([0.1], device="cuda"); bias = torch.randn(Cout, device="cuda")
 kw = dict(up2=up2, smod=smod, demod=demod, regions=1, noise=noise, noise_w=nw, ch_shift=bias, act=L.ACT_LRELU, slope=0.2, gain=1.4)
 out = E.conv(E.View(x), pw, engine="tc", **kw)
 torch.cuda.synchronize()
-for flags in (0, 1, 2, 3, 4, 7):
+for flags in (0, 1, 8, 16, 24, 7):
     L.lib().e4s_debug_halo_flags(flags)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); E.conv(E.View(x), pw, engine="tc", out=out, **kw); e1.record(); torch.cuda.synchronize()
