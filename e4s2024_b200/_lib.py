@@ -45,7 +45,7 @@ class E4SConv(C.Structure):
 
 
 EXPORTS = [
-    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc",
+    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs",
     "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
@@ -113,6 +113,22 @@ def conv(params: E4SConv, tc_weights: Optional[torch.Tensor] = None):
         _check(lib().e4s_conv_tc(C.byref(params), C.c_void_p(tc_weights.data_ptr()), _stream()), "e4s_conv_tc")
     else:
         _check(lib().e4s_conv_f32(C.byref(params), _stream()), "e4s_conv_f32")
+
+
+def conv_regions(params: E4SConv, tc_weights: torch.Tensor, jobs: torch.Tensor, count: torch.Tensor, count_host: int):
+    _check(lib().e4s_conv_tc_regions(C.byref(params), C.c_void_p(tc_weights.data_ptr()), C.c_void_p(jobs.data_ptr()),
+                                     C.c_void_p(count.data_ptr()), int(count_host), _stream()), "e4s_conv_tc_regions")
+
+
+def region_tile_jobs(labels: torch.Tensor, hout: int, wout: int, up2: bool, regions: int, count_slot: torch.Tensor):
+    """-> jobs int32 [max_jobs, 4]; count_slot: zeroed int32[1] view that receives the job count."""
+    b, lh, lw = labels.shape
+    gh, gw = (hout // 2, wout // 2) if up2 else (hout, wout)
+    max_jobs = b * (gh // 16) * (gw // 8) * min(regions, 32)
+    jobs = torch.empty(max_jobs, 4, dtype=torch.int32, device=labels.device)
+    _check(lib().e4s_region_tile_jobs(_fp(labels.data_ptr()), b, lh, lw, hout, wout, int(up2), _fp(jobs.data_ptr()),
+                                      _fp(count_slot.data_ptr()), max_jobs, _stream()), "e4s_region_tile_jobs")
+    return jobs
 
 
 def conv_batched(params_list):
@@ -183,12 +199,13 @@ def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
     return y
 
 
-def mask_labels(mask: torch.Tensor):
+def mask_labels(mask: torch.Tensor, flags: Optional[torch.Tensor] = None):
     """-> (labels u8 [B,H,W], flags int32[1]); flags[0] > 0 means the mask is not one-hot/empty per pixel."""
     _req(mask)
     b, k, h, w = mask.shape
     labels = torch.empty(b, h, w, device=mask.device, dtype=torch.uint8)
-    flags = torch.zeros(1, device=mask.device, dtype=torch.int32)
+    if flags is None:
+        flags = torch.zeros(1, device=mask.device, dtype=torch.int32)
     _check(lib().e4s_mask_labels(_fp(mask.data_ptr()), b, k, h, w, _fp(labels.data_ptr()), _fp(flags.data_ptr()), _stream()),
            "e4s_mask_labels")
     return labels, flags

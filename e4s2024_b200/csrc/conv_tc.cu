@@ -345,7 +345,8 @@ int validate_conv(const E4SConv* p);
 
 static int g_tc_halo = -1;         // -1: read E4S_TC_HALO (default on)
 bool tc_halo_eligible(const E4SConv* p);
-int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s);
+int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs, const int* rjob_count, int rjob_host_count);
+bool tc_halo_geometry_ok(const E4SConv* p);
 
 static bool tc_shape_ok(int k, int cout) {
   if (k < 8 || k % 8) return false;
@@ -410,7 +411,7 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
     const char* e = getenv("E4S_TC_HALO");
     g_tc_halo = (e && e[0] == '0') ? 0 : 1;
   }
-  if (g_tc_halo && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s);
+  if (g_tc_halo && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s, nullptr, nullptr, 0);
   switch (tc_block_n(p->cout)) {
     case 256: return launch_tc<256>(p, w_packed, m_total, s);
     case 128: return launch_tc<128>(p, w_packed, m_total, s);
@@ -418,4 +419,20 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
     case 32: return launch_tc<32>(p, w_packed, m_total, s);
     default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc: unsupported cout %d", p->cout);
   }
+}
+
+// Masked (regional) layer through the halo kernel: one job per (16x8 tile, region present) from e4s_region_tile_jobs.
+// `job_count` is the device counter the builder filled, `job_count_host` its value (the caller already read it back once
+// per forward to choose between this path and the per-row gather kernel).
+extern "C" int e4s_conv_tc_regions(const E4SConv* p, const void* w_packed, const int32_t* jobs, const int32_t* job_count, int job_count_host,
+                                   void* stream) {
+  int rc = validate_conv(p);
+  if (rc) return rc;
+  E4S_REQUIRE(w_packed && jobs && job_count && job_count_host > 0, "conv_tc_regions: null job list");
+  E4S_REQUIRE(p->labels && p->smod, "conv_tc_regions: needs labels and a style table");
+  const int K = p->kh * p->kw * p->cin;
+  E4S_REQUIRE(tc_shape_ok(K, p->cout) && tc_halo_geometry_ok(p), "conv_tc_regions: geometry not supported by the halo kernel");
+  E4S_REQUIRE(!p->in_square && !p->pixw, "conv_tc_regions: in_square / pixw are not supported here");
+  E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc_regions: out must be 16-byte aligned");
+  return tc_launch_halo(p, w_packed, as_stream(stream), reinterpret_cast<const int4*>(jobs), job_count, job_count_host);
 }

@@ -42,7 +42,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t 
 }
 
 struct HlJob {
-  int b, y0, x0, nt;
+  int b, y0, x0, nt, reg;
 };
 
 // optional timeline trace of CTA 0 (debug / profiling aid): records (role, job, event, clock64) when a buffer is installed
@@ -62,7 +62,7 @@ __device__ __forceinline__ void hl_trace(int role, int it, int ev) {
 template <int BN>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
-                    const int total_jobs) {
+                    const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count) {
   constexpr int BST = hl_b_stages(BN);
   constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of a packed 64-wide K chunk
   constexpr uint32_t IDESC = umma_idesc(BN);
@@ -93,13 +93,25 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   const int CPG = (9 + tpc - 1) / tpc;                       // packed chunks per (phase, group)
   const int num_kc = (9 * p.cin + 63) / 64;
   const int nsets = (2 * P * BN <= 512) ? 2 : 1;
-  const int my_jobs = (total_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // masked layers: one job per (tile, region present in the tile) from a device-built list (e4s_region_tile_jobs);
+  // the halo is modulated with that region's style and the epilogue keeps only the rows that belong to the region
+  const int total_jobs = rjobs ? __ldg(rjob_count) * n_tiles : total_jobs_in;
+  const int my_jobs = total_jobs > (int)blockIdx.x ? (total_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   auto decode = [&](int it) {
     int j = (int)blockIdx.x + it * (int)gridDim.x;
     HlJob r;
     r.nt = j % n_tiles;
     j /= n_tiles;
+    if (rjobs) {
+      const int4 jv = __ldg(rjobs + j);
+      r.b = jv.x;
+      r.y0 = jv.y;
+      r.x0 = jv.z;
+      r.reg = jv.w;
+      return r;
+    }
+    r.reg = 0;
     r.x0 = (j % tiles_x) * HL_TW;
     j /= tiles_x;
     r.y0 = (j % tiles_y) * HL_TH;
@@ -146,7 +158,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       const HlJob jb = decode(it);
       const int ch = g * 64 + cg * 8;
       if (p.smod) {
-        const float4* sp = reinterpret_cast<const float4*>(p.smod + (int64_t)jb.b * p.regions * p.cin + ch);
+        const float4* sp = reinterpret_cast<const float4*>(p.smod + ((int64_t)jb.b * p.regions + jb.reg) * p.cin + ch);
         sc[0] = __ldg(sp);
         sc[1] = __ldg(sp + 1);
       }
@@ -233,14 +245,19 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       const int set = nsets == 2 ? (it & 1) : 0;
       const int use = nsets == 2 ? (it >> 1) : it;
       // per-pixel epilogue operands (noise / float-mask loads) are fetched BEFORE waiting for the accumulator
-      const float* drow = p.demod ? p.demod + (int64_t)jb.b * p.regions * p.cout : nullptr;
+      const float* drow = p.demod ? p.demod + ((int64_t)jb.b * p.regions + jb.reg) * p.cout : nullptr;
       TcEpiRow er[4];
+      uint32_t rowlive = 0xf;                                   // per phase: does this row (pixel) belong to the job's region
 #pragma unroll
       for (int ph = 0; ph < 4; ++ph) {
         if (ph >= P) break;
         const int oy = up ? 2 * (jb.y0 + ty) + (ph >> 1) : jb.y0 + ty;
         const int ox = up ? 2 * (jb.x0 + tx) + (ph & 1) : jb.x0 + tx;
         er[ph].pix = ((int64_t)jb.b * p.hout + oy) * p.wout + ox;
+        if (rjobs) {
+          const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
+          if (p.labels[((int64_t)jb.b * p.lab_h + sy) * p.lab_w + sx] != jb.reg) rowlive &= ~(1u << ph);
+        }
         er[ph].drow = drow;
         er[ph].pw = 1.f;
         if (p.pixw) {
@@ -279,7 +296,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.f;
           }
-          if (!(dbg & 1)) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph], dbg);
+          if (!(dbg & 1) && (rowlive & (1u << ph))) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph], dbg);
         }
       }
       tc_fence_before();
@@ -375,13 +392,50 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   }
 }
 
+// One CTA per 16x8 tile: which regions own at least one of the tile's output pixels?  Appends one int4 job
+// (b, y0, x0, region) per region present.  up2: the tile is over INPUT pixels and covers 32x16 output pixels.
+__global__ void __launch_bounds__(128) region_tile_jobs_kernel(const uint8_t* __restrict__ labels, int lab_h, int lab_w, int hout,
+                                                               int wout, int up2, int tiles_x, int tiles_y, int4* __restrict__ jobs,
+                                                               int* __restrict__ count, int max_jobs) {
+  __shared__ uint32_t present;
+  if (threadIdx.x == 0) present = 0;
+  __syncthreads();
+  int t = blockIdx.x;
+  const int txi = t % tiles_x;
+  t /= tiles_x;
+  const int tyi = t % tiles_y;
+  const int b = t / tiles_y;
+  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  uint32_t mine = 0;
+  const int np = up2 ? 4 : 1;
+  for (int ph = 0; ph < np; ++ph) {
+    const int oy = up2 ? 2 * (tyi * HL_TH + ty) + (ph >> 1) : tyi * HL_TH + ty;
+    const int ox = up2 ? 2 * (txi * HL_TW + tx) + (ph & 1) : txi * HL_TW + tx;
+    const int sy = nearest_src(oy, lab_h, hout), sx = nearest_src(ox, lab_w, wout);
+    mine |= 1u << (labels[((int64_t)b * lab_h + sy) * lab_w + sx] & 31);
+  }
+  atomicOr(&present, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t m = present;
+    const int n = __popc(m);
+    const int base = atomicAdd(count, n);
+    int i = 0;
+    while (m) {
+      const int r = __ffs(m) - 1;
+      m &= m - 1;
+      if (base + i < max_jobs) jobs[base + i] = make_int4(b, tyi * HL_TH, txi * HL_TW, r);
+      ++i;
+    }
+  }
+}
+
 static int g_halo_sm_count = 0;
 
 // geometry the halo kernel takes (everything else stays on the gather kernel)
-bool tc_halo_eligible(const E4SConv* p) {
+bool tc_halo_geometry_ok(const E4SConv* p) {
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   if (!up && !(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && p->in_shift == 0)) return false;
-  if (p->labels) return false;                               // per-pixel regions need the per-row gather path
   if (p->hin % HL_TH || p->win % HL_TW) return false;
   if (!(p->cin == 32 || p->cin % 64 == 0)) return false;
   const int bn = tc_block_n(p->cout);
@@ -389,8 +443,14 @@ bool tc_halo_eligible(const E4SConv* p) {
   return true;
 }
 
+bool tc_halo_eligible(const E4SConv* p) {
+  if (p->labels) return false;                               // per-pixel regions: region-job list (e4s_conv_tc_regions) or gather
+  return tc_halo_geometry_ok(p);
+}
+
 template <int BN>
-static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
+static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs = nullptr, const int* rjob_count = nullptr,
+                       int rjob_host_count = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl_smem_bytes(BN));
@@ -404,11 +464,11 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
     if (g_halo_sm_count <= 0) g_halo_sm_count = 148;
   }
   const int tiles_x = p->win / HL_TW, tiles_y = p->hin / HL_TH, n_tiles = p->cout / BN;
-  const int64_t total = (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
-  E4S_REQUIRE(total < 0x7fffffff, "conv_tc(halo): too many tiles");
+  const int64_t total = rjobs ? (int64_t)rjob_host_count * n_tiles : (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
+  E4S_REQUIRE(total > 0 && total < 0x7fffffff, "conv_tc(halo): bad job count");
   const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
   conv_tc_halo_kernel<BN><<<grid, HL_THREADS, hl_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
-                                                                     (int)total);
+                                                                     (int)total, rjobs, rjob_count);
   return check_launch("e4s_conv_tc(halo)");
 }
 
@@ -426,17 +486,30 @@ int tc_halo_set_trace(void* buf, int cap_records) {
   return e == cudaSuccess ? E4S_OK : fail(E4S_ERR_CUDA, "halo trace: %s", cudaGetErrorString(e));
 }
 
-int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s) {
+int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs, const int* rjob_count, int rjob_host_count) {
   switch (tc_block_n(p->cout)) {
-    case 256: return launch_halo<256>(p, wpk, s);
-    case 128: return launch_halo<128>(p, wpk, s);
-    case 64: return launch_halo<64>(p, wpk, s);
-    case 32: return launch_halo<32>(p, wpk, s);
+    case 256: return launch_halo<256>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 128: return launch_halo<128>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 64: return launch_halo<64>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 32: return launch_halo<32>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
     default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc(halo): unsupported cout %d", p->cout);
   }
 }
 
 }  // namespace e4s
+
+extern "C" int e4s_region_tile_jobs(const uint8_t* labels, int batch, int lab_h, int lab_w, int hout, int wout, int up2, int32_t* jobs,
+                                    int32_t* count, int max_jobs, void* stream) {
+  using namespace e4s;
+  E4S_REQUIRE(labels && jobs && count && batch > 0 && lab_h > 0 && lab_w > 0 && hout > 0 && wout > 0 && max_jobs > 0, "region_tile_jobs: bad args");
+  const int gh = up2 ? hout / 2 : hout, gw = up2 ? wout / 2 : wout;
+  E4S_REQUIRE(gh % HL_TH == 0 && gw % HL_TW == 0 && (!up2 || (hout % 2 == 0 && wout % 2 == 0)), "region_tile_jobs: %dx%d is not tileable by 16x8", gh, gw);
+  E4S_REQUIRE((reinterpret_cast<uintptr_t>(jobs) & 15) == 0, "region_tile_jobs: jobs must be 16-byte aligned");
+  const int tiles_x = gw / HL_TW, tiles_y = gh / HL_TH;
+  region_tile_jobs_kernel<<<(unsigned)(batch * tiles_x * tiles_y), 128, 0, as_stream(stream)>>>(labels, lab_h, lab_w, hout, wout, up2, tiles_x,
+                                                                                              tiles_y, reinterpret_cast<int4*>(jobs), count, max_jobs);
+  return check_launch("region_tile_jobs");
+}
 
 // debug aid (not part of the reference-facing surface): install / remove a clock64 timeline buffer for CTA 0 of the halo kernel
 extern "C" int e4s_debug_halo_trace(void* buf, int cap_records) { return e4s::tc_halo_set_trace(buf, cap_records); }

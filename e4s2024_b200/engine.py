@@ -53,6 +53,15 @@ class PackedConv:
         return self.kh * self.kw * self.cin
 
 
+def halo_geometry_ok(cin: int, cout: int, hin: int, win: int, up2: bool, kh: int = 3, stride: int = 1) -> bool:
+    """Mirror of tc_halo_geometry_ok (conv_tc_halo.cu): what the halo kernel takes."""
+    if kh != 3 or stride != 1 or hin % 16 or win % 8:
+        return False
+    if not (cin == 32 or cin % 64 == 0):
+        return False
+    return (4 if up2 else 1) * min(cout, 256) <= 512 and tc_eligible(cin, cout)
+
+
 def tc_eligible(cin: int, cout: int) -> bool:
     return cin % 8 == 0 and (cout in (32, 64, 128) or (cout >= 256 and cout % 256 == 0))
 
@@ -147,7 +156,8 @@ def new_nhwc(b, h, w, c, device) -> torch.Tensor:
 def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, in_stats=None, in_square=False,
          smod=None, demod=None, labels=None, regions=1, smod_off=0, demod_off=0, pixw=None, ch_scale=None, ch_shift=None,
          noise=None, noise_w=None, res: Optional[View] = None, res_after_act=False, act=L.ACT_NONE, slope=0.0, gain=1.0,
-         prelu=None, out: Optional[View] = None, accumulate=False, engine: Optional[str] = None) -> View:
+         prelu=None, out: Optional[View] = None, accumulate=False, engine: Optional[str] = None,
+         region_jobs: Optional["RegionJobs"] = None) -> View:
     """Launch one fused convolution (see struct E4SConv).  Returns the output view."""
     b, hin, win = x.bhw
     assert x.c == pw.cin, (x.c, pw.cin)
@@ -204,17 +214,25 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     p.out, p.out_pitch, p.accumulate = out.ptr, out.pitch, int(accumulate)
     eng = engine or _ENGINE
     use_tc = eng == "tc" and pw.tc is not None
+    use_rj = use_tc and region_jobs is not None and labels is not None
+
+    def launch():
+        if use_rj:
+            L.conv_regions(p, pw.tc, region_jobs.jobs, region_jobs.count_dev, region_jobs.count)
+        else:
+            L.conv(p, pw.tc if use_tc else None)
+
     if PROFILE is None:
-        L.conv(p, pw.tc if use_tc else None)
+        launch()
         return out
     # bench.py's per-launch timing pass: CUDA events on the launching stream around this one kernel
     m_exec = b * hout * wout
     alg = 2.0 * (m_exec / 4 if up2 else m_exec) * pw.k * pw.cout      # conv_transpose counted at input resolution
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    L.conv(p, pw.tc if use_tc else None)
+    launch()
     ev1.record()
-    PROFILE.append({"engine": "tc" if use_tc else "f32", "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
+    PROFILE.append({"engine": "tc" if use_tc else "f32", "region_jobs": region_jobs.count if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
                     "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1),
                     "bytes": 4.0 * (b * hin * win * pw.cin + m_exec * pw.cout)})
     return out
@@ -249,18 +267,49 @@ def linear_rows(x_ptr_tensor: torch.Tensor, rows: int, row_stride: int, offset: 
     return out
 
 
+REGION_JOB_RATIO = float(os.environ.get("E4S_REGION_RATIO", "3.0"))
+
+
+@dataclass
+class RegionJobs:
+    """(16x8 tile, region present) job list of one masked layer resolution (e4s_region_tile_jobs)."""
+    jobs: torch.Tensor
+    count_dev: torch.Tensor
+    count: int
+    tiles: int
+
+
 class RegionCtx:
     """Per-forward view of the mask [B,K,Hm,Wm]: u8 label map when every pixel has at most one
-    region with weight exactly 1 (the pipelines' one-hot masks), else the generic float path."""
+    region with weight exactly 1 (the pipelines' one-hot masks), else the generic float path.
+    `job_keys` = [(hout, wout, up2)] of the masked 3x3 layers whose geometry the halo kernel takes: their
+    per-tile region job lists are built here and the counts come back in the same (single) D2H read as the flag."""
 
-    def __init__(self, mask: torch.Tensor):
+    def __init__(self, mask: torch.Tensor, job_keys=()):
         if mask.dim() != 4:
             raise L.E4SError("mask must be [B,K,H,W]")
         self.mask = mask.contiguous().float()
         self.k = mask.shape[1]
-        self.labels, flags = L.mask_labels(self.mask)
-        self.onehot = int(flags.item()) == 0          # 4-byte D2H read, once per forward
+        keys = list(dict.fromkeys(job_keys)) if (self.mask.is_cuda and self.k <= 32 and tc_available()) else []
+        meta = torch.zeros(1 + len(keys), device=self.mask.device, dtype=torch.int32)
+        self.labels, _ = L.mask_labels(self.mask, meta[0:1])
+        lists = [L.region_tile_jobs(self.labels, h, w, up, self.k, meta[1 + i:2 + i]) for i, (h, w, up) in enumerate(keys)]
+        host = meta.cpu()                               # one small D2H read per forward
+        self.onehot = int(host[0]) == 0
         self.regions = self.k
+        self.region_jobs = {}
+        b = self.mask.shape[0]
+        for i, (key, jl) in enumerate(zip(keys, lists)):
+            h, w, up = key
+            gh, gw = (h // 2, w // 2) if up else (h, w)
+            self.region_jobs[key] = RegionJobs(jl, meta[1 + i:2 + i], int(host[1 + i]), b * (gh // 16) * (gw // 8))
+
+    def jobs_for(self, hout: int, wout: int, up2: bool) -> Optional["RegionJobs"]:
+        """The job list if this resolution has few enough regions per tile for the halo kernel to win."""
+        rj = self.region_jobs.get((hout, wout, bool(up2)))
+        if rj is None or not self.onehot or rj.count <= 0 or rj.count > REGION_JOB_RATIO * rj.tiles:
+            return None
+        return rj
 
     @property
     def lab_hw(self):

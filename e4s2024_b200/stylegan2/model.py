@@ -198,8 +198,13 @@ class ModulatedConv2d(nn.Module):
         if regional and ctx is None:
             raise L.E4SError("regional styles need a mask")
         if not regional or ctx.onehot:
+            rj = None
+            if regional:
+                _, h, w = x.bhw
+                ho, wo = (2 * h, 2 * w) if self.upsample else (h, w)
+                rj = ctx.jobs_for(ho, wo, self.upsample)
             return E.conv(x, conv, up2=self.upsample, smod=s, demod=d, regions=st.regions,
-                          labels=ctx.labels if regional else None, **epilogue)
+                          labels=ctx.labels if regional else None, region_jobs=rj, **epilogue)
         # generic float masks: sum_k mask_k * conv(x; style_k), then the epilogue (model.py:395-398)
         out = None
         for r in range(st.regions):
@@ -374,6 +379,18 @@ class Generator(nn.Module):
             in_channel = out_channel
         self.n_latent = self.log_size * 2 - 2
 
+    def _region_job_keys(self):
+        """(hout, wout, up2) of the masked StyledConv layers whose geometry the halo kernel takes."""
+        keys = []
+        res = 4
+        for conv_up, conv2 in zip(self.convs[::2], self.convs[1::2]):
+            res *= 2
+            if conv_up.mask_op and E.halo_geometry_ok(conv_up.conv.in_channel, conv_up.conv.out_channel, res // 2, res // 2, True):
+                keys.append((res, res, True))
+            if conv2.mask_op and E.halo_geometry_ok(conv2.conv.in_channel, conv2.conv.out_channel, res, res, False):
+                keys.append((res, res, False))
+        return keys
+
     def make_noise(self):
         device = self.input.input.device
         noises = [torch.randn(1, 1, 2 ** 2, 2 ** 2, device=device)]
@@ -408,7 +425,7 @@ class Generator(nn.Module):
         b, k, nl, sd = latent.shape
         if sd != self.style_dim or nl < self.n_latent:
             raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
-        ctx = E.RegionCtx(mask.to(latent.device))
+        ctx = E.RegionCtx(mask.to(latent.device), self._region_job_keys())
         if ctx.k != k or ctx.mask.shape[0] != b:
             raise L.E4SError("mask and latent disagree on batch / number of regions")
 

@@ -112,6 +112,15 @@ int e4s_conv_f32_batched(const E4SConv* params, int count, void* stream);
 /* tcgen05 (5th-gen tensor core) implicit GEMM with the 3-pass bf16 hi/lo split (fp32 accumulate in TMEM).
  * w points to the packed bf16 image produced by e4s_pack_weights_tc; cin % 8 == 0, cout in {32,64,128,256*n}. */
 int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream);
+/* Regional (masked) 3x3 / up-conv layer through the halo kernel: `jobs` holds one int4 (b, y0, x0, region) per (16x8 tile,
+ * region present in the tile), built on the device by e4s_region_tile_jobs; job_count is the device counter, job_count_host
+ * its value.  Every output pixel is written by exactly one job (the one of its own region). */
+int e4s_conv_tc_regions(const E4SConv* p, const void* w_packed, const int32_t* jobs, const int32_t* job_count, int job_count_host,
+                        void* stream);
+/* labels u8 [batch, lab_h, lab_w] -> job list for an hout x wout layer (up2: tiles over the hout/2 x wout/2 input grid);
+ * *count must be zeroed by the caller and receives the number of jobs (entries beyond max_jobs are dropped) */
+int e4s_region_tile_jobs(const uint8_t* labels, int batch, int lab_h, int lab_w, int hout, int wout, int up2, int32_t* jobs,
+                         int32_t* count, int max_jobs, void* stream);
 /* bytes needed for the packed tensor-core weights of a [phases, K, cout] fp32 matrix */
 int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);
 /* w_f32: [phases][K = taps*cin][cout_pad] (the e4s_conv_f32 layout) -> w_packed (hi/lo bf16, UMMA K-major SW128 tiles;

@@ -174,12 +174,15 @@ def nhwc_to_nchw(x, c=None):
     return x[..., :c].permute(0, 3, 1, 2).contiguous()
 
 
-def mask_labels(mask):
+def mask_labels(mask, flags=None):
     nonzero = (mask != 0).sum(1)
     ones = (mask == 1).sum(1)
     bad = ~((nonzero == 1) & (ones == 1))
     labels = mask.argmax(1).to(torch.uint8)
-    return labels.contiguous(), torch.tensor([int(bad.any())], dtype=torch.int32)
+    if flags is None:
+        flags = torch.zeros(1, dtype=torch.int32)
+    flags[0] = int(bad.any())
+    return labels.contiguous(), flags
 
 
 def labels_to_onehot(labels, k):

@@ -1,0 +1,47 @@
+"""GPU: masked layers through the halo kernel's region-job path (one job per (16x8 tile, region present)) must give the
+same result as the per-row gather path, and both must match the oracle."""
+import pytest
+import torch
+
+from e4s2024_b200 import synth
+from oracle import e4s_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("up", [False, True])
+def test_region_jobs_match_gather_and_oracle(up):
+    from e4s2024_b200 import engine as E
+    from e4s2024_b200.stylegan2.model import StyledConv
+    if not E.tc_available():
+        pytest.skip("no tcgen05 engine")
+    K, B, cin, cout, res = 5, 2, 128, 64, 32
+    m = StyledConv(cin, cout, 3, 512, upsample=up, mask_op=True)
+    sd = synth.synth_module_weights(m, seed=31)
+    m = m.cuda()
+    x = synth.randn("rj.x", (B, cin, res, res), 31)
+    style = synth.randn("rj.s", (B, K, 512), 31)
+    out_res = 2 * res if up else res
+    lab = synth.blocky_labels(B, K, 128, cells=8, seed=31)           # 16-px cells at 128^2 -> few regions per tile
+    mask = synth.onehot(lab, K)
+    noise = synth.randn("rj.n", (1, 1, out_res, out_res), 31)
+    ref = orc.styled_conv(x, style, mask, {k: v.cpu() for k, v in sd.items()}, "", upsample=up, mask_op=True, noise=noise)
+
+    old = E.REGION_JOB_RATIO
+    try:
+        E.REGION_JOB_RATIO = 1e9                                       # force the region-job path
+        key = (out_res, out_res, up)
+        ctx = E.RegionCtx(mask.cuda(), [key])
+        assert ctx.onehot and ctx.jobs_for(*key) is not None and ctx.region_jobs[key].count >= ctx.region_jobs[key].tiles
+        from e4s2024_b200 import _lib as L
+        from e4s2024_b200.stylegan2.model import StyleRows
+        xin = E.View(L.nchw_to_nhwc(x.cuda()))
+        y_rj = L.nhwc_to_nchw(m.run(xin, StyleRows.from_tensor(style.cuda()), ctx, noise.cuda()).t)
+        E.REGION_JOB_RATIO = 0.0                                       # force the per-row gather path
+        y_g = L.nhwc_to_nchw(m.run(xin, StyleRows.from_tensor(style.cuda()), ctx, noise.cuda()).t)
+    finally:
+        E.REGION_JOB_RATIO = old
+    d_rj = float((y_rj.cpu() - ref).abs().max())
+    d_g = float((y_g.cpu() - ref).abs().max())
+    print(f"up={up}: region-job path vs oracle {d_rj:.3e}, gather path vs oracle {d_g:.3e}, jobs {ctx.region_jobs[key].count} / tiles {ctx.region_jobs[key].tiles}")
+    assert d_rj < 5e-4 and d_g < 5e-4
