@@ -32,10 +32,16 @@ constexpr int HL_THREADS = 14 * 32;
 constexpr int HL_MMA_WARP = 12;             // warps 8-11 epilogue, 12 MMA issuer, 13 weight loader
 constexpr int HL_ITEMS = (HL_HPIX + 31) / 32;     // 6 (pixel, 8-channel) items per producer thread
 
-__host__ __device__ constexpr int hl_b_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 4 : 6); }
-__host__ __device__ constexpr int hl_smem_bytes(int bn) {
-  return HL_HALO_STAGES * 2 * HL_PLANE + hl_b_stages(bn) * 2 * bn * 128 + 2 * 3 * bn * 4 + 512 + 1024;
+constexpr int HL_MAX_BST = 6;
+constexpr int HL_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
+// phases of an up-convolution merged into the N dimension of one MMA (all four phases read the SAME halo window)
+__host__ __device__ constexpr int hl_phase_merge(int bn, bool up) { return (up && 4 * bn <= 256) ? 4 : 1; }
+__host__ __device__ constexpr int hl_fixed_bytes(int bn) { return HL_HALO_STAGES * 2 * HL_PLANE + 2 * 3 * bn * 4 + 512 + 1024; }
+__host__ __device__ constexpr int hl_b_stages(int bn, int pm) {
+  int n = (HL_SMEM_MAX - hl_fixed_bytes(bn)) / (2 * pm * bn * 128);
+  return n > HL_MAX_BST ? HL_MAX_BST : n;
 }
+__host__ __device__ constexpr int hl_smem_bytes(int bn, int pm) { return hl_fixed_bytes(bn) + hl_b_stages(bn, pm) * 2 * pm * bn * 128; }
 
 __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -63,9 +69,12 @@ template <int BN>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
                     const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count) {
-  constexpr int BST = hl_b_stages(BN);
-  constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of a packed 64-wide K chunk
-  constexpr uint32_t IDESC = umma_idesc(BN);
+  constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of one phase of a packed 64-wide K chunk
+  const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
+  const int PM = hl_phase_merge(BN, up);          // phases merged into one MMA (N = PM * BN)
+  const int BST = hl_b_stages(BN, PM);
+  const int STAGE_B = 2 * PM * B_BYTES;           // [hi: PM x BN rows][lo: PM x BN rows]
+  const uint32_t IDESC = umma_idesc(PM * BN);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -73,19 +82,19 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   // [halo stage 0: hi | lo][halo stage 1: hi | lo][B ring: BST x (hi | lo)][barriers]
   constexpr int HALO_BYTES = 2 * HL_PLANE;
   constexpr int B_OFF = HL_HALO_STAGES * HALO_BYTES;
-  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * 2 * B_BYTES);        // [2 slots][mul | add | prelu][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * 2 * B_BYTES + 2 * 3 * BN * 4);
+  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * STAGE_B);            // [2 slots][mul | add | prelu][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * STAGE_B + 2 * 3 * BN * 4);
   const uint32_t bar_hfull = smem_u32(bars);                 // 2
   const uint32_t bar_hempty = bar_hfull + 16;                // 2
-  const uint32_t bar_bfull = bar_hempty + 16;                // BST
-  const uint32_t bar_bempty = bar_bfull + 8 * BST;           // BST
-  const uint32_t bar_afull = bar_bempty + 8 * BST;           // 2
+  const uint32_t bar_bfull = bar_hempty + 16;                // up to HL_MAX_BST
+  const uint32_t bar_bempty = bar_bfull + 8 * HL_MAX_BST;
+  const uint32_t bar_afull = bar_bempty + 8 * HL_MAX_BST;    // 2
   const uint32_t bar_aempty = bar_afull + 16;                // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * BST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * HL_MAX_BST);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
   const int P = up ? 4 : 1;
+  const int PL = P / PM;                                      // MMA groups of PM merged phases
   const int cin_eff = p.cin < 64 ? p.cin : 64;               // channels per halo row actually used
   const int G = p.cin < 64 ? 1 : p.cin / 64;                 // 64-channel groups
   const int ksteps = cin_eff / 16;
@@ -112,6 +121,14 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       return r;
     }
     r.reg = 0;
+    if (((tiles_x & (tiles_x - 1)) | (tiles_y & (tiles_y - 1))) == 0) {   // power-of-two grids: shifts instead of divisions
+      const int sx = 31 - __clz(tiles_x), sy = 31 - __clz(tiles_y);
+      r.x0 = (j & (tiles_x - 1)) * HL_TW;
+      j >>= sx;
+      r.y0 = (j & (tiles_y - 1)) * HL_TH;
+      r.b = j >> sy;
+      return r;
+    }
     r.x0 = (j % tiles_x) * HL_TW;
     j /= tiles_x;
     r.y0 = (j % tiles_y) * HL_TH;
@@ -126,7 +143,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 4);
     }
-    for (int s = 0; s < BST; ++s) {
+    for (int s = 0; s < HL_MAX_BST; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
       mbar_init(bar_bempty + 8 * s, 1);
     }
@@ -320,32 +337,33 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
           if (lane == 0) hl_trace(2, it, 2);
           tc_fence_after();
-          const uint32_t h_hi = smem_base + hs * HALO_BYTES, h_lo = h_hi + HL_PLANE;
-          for (int ph = 0; ph < P; ++ph) {
-            const uint32_t tacc = tmem_base + (uint32_t)((set * P + ph) * BN);
+          const uint32_t h_hi = smem_base + hs * HALO_BYTES;
+          // descriptors are affine in the byte address: desc(a + off) = desc(a) + (off >> 4)  (14-bit field, smem < 256 KB)
+          const uint64_t dah0 = umma_smem_desc_sbo(h_hi, HL_HP * 128), dal0 = umma_smem_desc_sbo(h_hi + HL_PLANE, HL_HP * 128);
+          for (int pl = 0; pl < PL; ++pl) {
+            const uint32_t tacc = tmem_base + (uint32_t)((set * P + pl * PM) * BN);
             for (int c = 0; c < CPG; ++c, ++bc) {
               const int bs = bc % BST;
               mbar_wait(bar_bfull + 8 * bs, (bc / BST) & 1);
               tc_fence_after();
-              const uint32_t b_hi = smem_base + B_OFF + bs * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
-              for (int tt = 0; tt < tpc; ++tt) {
-                const int tap = c * tpc + tt;
-                if (tap >= 9) break;
-                const uint32_t aoff = (uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u;
-                const uint32_t boff = (uint32_t)(tt * cin_eff * 2);
-                if (!(g_hl_dbg & 4) && elect_one()) {
+              const uint32_t b_hi = smem_base + B_OFF + bs * STAGE_B;
+              const uint64_t dbh0 = umma_smem_desc(b_hi), dbl0 = umma_smem_desc(b_hi + PM * B_BYTES);
+              if (!(g_hl_dbg & 4) && elect_one()) {
+                for (int tt = 0; tt < tpc; ++tt) {
+                  const int tap = c * tpc + tt;
+                  if (tap >= 9) break;
+                  const uint32_t aoff = ((uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u) >> 4;
+                  const uint32_t boff = (uint32_t)(tt * cin_eff * 2) >> 4;
                   for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t dah = umma_smem_desc_sbo(h_hi + aoff + k * 32, HL_HP * 128);
-                    const uint64_t dal = umma_smem_desc_sbo(h_lo + aoff + k * 32, HL_HP * 128);
-                    const uint64_t dbh = umma_smem_desc(b_hi + boff + k * 32), dbl = umma_smem_desc(b_lo + boff + k * 32);
+                    const uint64_t dah = dah0 + aoff + 2 * k, dal = dal0 + aoff + 2 * k;
+                    const uint64_t dbh = dbh0 + boff + 2 * k, dbl = dbl0 + boff + 2 * k;
                     umma_bf16(tacc, dal, dbh, IDESC, (g | tap | k) != 0);
                     umma_bf16(tacc, dah, dbl, IDESC, 1);
                     umma_bf16(tacc, dah, dbh, IDESC, 1);
                   }
                 }
-                __syncwarp();
+                umma_commit(bar_bempty + 8 * bs);
               }
-              if (elect_one()) umma_commit(bar_bempty + 8 * bs);
               __syncwarp();
             }
           }
@@ -366,19 +384,22 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       for (int it = 0; it < my_jobs; ++it) {
         const HlJob jb = decode(it);
         for (int g = 0; g < G; ++g)
-          for (int ph = 0; ph < P; ++ph) {
-            const uint8_t* src = wpk + ((int64_t)ph * n_tiles + jb.nt) * num_kc * tile_bytes;
+          for (int pl = 0; pl < PL; ++pl)
             for (int c = 0; c < CPG; ++c, ++bc) {
               const int bs = bc % BST;
               const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
               mbar_wait(bar_bempty + 8 * bs, ((bc / BST) & 1) ^ 1);
               if (elect_one()) {
-                mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * B_BYTES);
-                bulk_g2s(smem_base + B_OFF + bs * 2 * B_BYTES, src + kc * tile_bytes, 2 * B_BYTES, bar_bfull + 8 * bs);
+                const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
+                for (int q = 0; q < PM; ++q) {               // hi tiles of the merged phases back to back, then the lo tiles
+                  const uint8_t* src = wpk + (((int64_t)(pl * PM + q) * n_tiles + jb.nt) * num_kc + kc) * tile_bytes;
+                  bulk_g2s(dst + q * B_BYTES, src, B_BYTES, bar_bfull + 8 * bs);
+                  bulk_g2s(dst + (PM + q) * B_BYTES, src + B_BYTES, B_BYTES, bar_bfull + 8 * bs);
+                }
               }
               __syncwarp();
             }
-          }
       }
     }
     __syncwarp();
@@ -452,8 +473,10 @@ template <int BN>
 static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs = nullptr, const int* rjob_count = nullptr,
                        int rjob_host_count = 0) {
   static bool attr_set = false;
+  const int pm = hl_phase_merge(BN, p->mode == E4S_CONV_UP2_POLYPHASE);
+  const int smem_bytes = hl_smem_bytes(BN, pm);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hl_smem_bytes(BN));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX);
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -467,7 +490,7 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
   const int64_t total = rjobs ? (int64_t)rjob_host_count * n_tiles : (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
   E4S_REQUIRE(total > 0 && total < 0x7fffffff, "conv_tc(halo): bad job count");
   const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
-  conv_tc_halo_kernel<BN><<<grid, HL_THREADS, hl_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
+  conv_tc_halo_kernel<BN><<<grid, HL_THREADS, smem_bytes, s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
                                                                      (int)total, rjobs, rjob_count);
   return check_launch("e4s_conv_tc(halo)");
 }
