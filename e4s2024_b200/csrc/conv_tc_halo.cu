@@ -348,8 +348,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               tc_fence_after();
               const uint32_t b_hi = smem_base + B_OFF + bs * STAGE_B;
               const uint64_t dbh0 = umma_smem_desc(b_hi), dbl0 = umma_smem_desc(b_hi + PM * B_BYTES);
-              if (!(g_hl_dbg & 4) && elect_one()) {
-                for (int tt = 0; tt < tpc; ++tt) {
+              if (elect_one()) {
+                for (int tt = 0; tt < ((g_hl_dbg & 4) ? 0 : tpc); ++tt) {
                   const int tap = c * tpc + tt;
                   if (tap >= 9) break;
                   const uint32_t aoff = ((uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u) >> 4;
