@@ -199,7 +199,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       }
     };
 
-    prefetch(0);
+    const int pdbg = g_hl_dbg;
+    if (!(pdbg & 32)) prefetch(0);
     for (int hg = 0; hg < total_hg; ++hg) {
       const int hs = hg & 1;
       if (tid == 0) hl_trace(0, hg, 0);
@@ -207,7 +208,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       if (tid == 0) hl_trace(0, hg, 1);
       uint8_t* h_hi = smem + hs * HALO_BYTES;
       uint8_t* h_lo = h_hi + HL_PLANE;
-      if (cg_live) {
+      if (cg_live && !(pdbg & 32)) {
 #pragma unroll
         for (int i = 0; i < HL_ITEMS; ++i) {
           const int px = px0 + 32 * i;
@@ -247,7 +248,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
-      prefetch(hg + 1);
+      if (!(pdbg & 32)) prefetch(hg + 1);
       if (tid == 0) hl_trace(0, hg, 3);
     }
   } else if (warp < HL_MMA_WARP) {
@@ -389,7 +390,9 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               const int bs = bc % BST;
               const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
               mbar_wait(bar_bempty + 8 * bs, ((bc / BST) & 1) ^ 1);
-              if (elect_one()) {
+              if (g_hl_dbg & 64) {
+                if (elect_one()) mbar_arrive(bar_bfull + 8 * bs);
+              } else if (elect_one()) {
                 const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
                 mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
                 for (int q = 0; q < PM; ++q) {               // hi tiles of the merged phases back to back, then the lo tiles
