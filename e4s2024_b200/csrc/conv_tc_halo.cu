@@ -51,30 +51,60 @@ struct HlJob {
   int b, y0, x0, nt, reg;
 };
 
-// optional timeline trace of CTA 0 (debug / profiling aid): records (role, job, event, clock64) when a buffer is installed
+// optional cycle accounting of CTA 0 (profiling aid): one lead thread per role adds the clock64 time between consecutive
+// laps to a shared-memory counter [role][lap]; the totals are written to the installed buffer when the kernel ends.  Unlike
+// a global-memory event trace this costs a few cycles per lap, so the numbers are those of the undisturbed kernel.
 __device__ unsigned long long* g_hl_trace = nullptr;
 __device__ int g_hl_trace_cap = 0;
-__device__ int g_hl_trace_n = 0;
 __device__ int g_hl_dbg = 0;      // profiling experiments: bit0 skip epilogue math+stores, bit1 skip tcgen05.ld, bit2 skip MMAs
-__device__ __forceinline__ void hl_trace(int role, int it, int ev) {
-  if (g_hl_trace == nullptr || blockIdx.x != 0) return;
-  const int i = atomicAdd(&g_hl_trace_n, 1);
-  if (i < g_hl_trace_cap) {
-    g_hl_trace[2 * i] = ((unsigned long long)role << 48) | ((unsigned long long)(it & 0xffffff) << 16) | (unsigned long long)ev;
-    g_hl_trace[2 * i + 1] = clock64();
-  }
+#define HL_LAP(role, k)                                   \
+  do {                                                    \
+    if (acct) {                                           \
+      const long long n_ = clock64();                     \
+      s_acct[(role) * 8 + (k)] += n_ - acct_t;            \
+      acct_t = n_;                                        \
+    }                                                     \
+  } while (0)
+
+// UMMA descriptor words.  The 64-bit shared-memory descriptor is affine in the byte address through its low word only
+// (14-bit start-address field in 16-byte units, smem < 256 KB => no carry), so the issue loop does 32-bit adds on the low
+// word and the high word (SBO, version, swizzle mode) is a constant.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(HL_THREADS, 1)
+template <int BN, bool UP>
+__global__ void __launch_bounds__(HL_THREADS, 1)   // 14 warps are allocated as 16: 128 registers per thread is the ceiling
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
                     const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count) {
   constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of one phase of a packed 64-wide K chunk
-  const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
-  const int PM = hl_phase_merge(BN, up);          // phases merged into one MMA (N = PM * BN)
-  const int BST = hl_b_stages(BN, PM);
-  const int STAGE_B = 2 * PM * B_BYTES;           // [hi: PM x BN rows][lo: PM x BN rows]
-  const uint32_t IDESC = umma_idesc(PM * BN);
+  constexpr int P = UP ? 4 : 1;
+  constexpr int PM = hl_phase_merge(BN, UP);      // phases merged into one MMA (N = PM * BN)
+  constexpr int PL = P / PM;                      // MMA groups of PM merged phases
+  constexpr int BST = hl_b_stages(BN, PM);
+  constexpr int STAGE_B = 2 * PM * B_BYTES;       // [hi: PM x BN rows][lo: PM x BN rows]
+  constexpr uint32_t IDESC = umma_idesc(PM * BN);
+  // same-resolution layers with BN <= 64: the hi and lo weight tiles of a stage are adjacent rows of one operand, so
+  // A_hi x [B_hi ; B_lo] is ONE MMA with N = 2*BN (two accumulator halves, summed in the epilogue) followed by A_lo x B_hi:
+  // 2 instead of 3 MMAs per K step (an M=128 MMA costs the same ~61 cycles for every N <= 128, profiles/r1_umma_rate_experiment.txt)
+  constexpr bool NC = !UP && BN <= 64;
+  constexpr uint32_t IDESC2 = umma_idesc(2 * BN <= 256 ? 2 * BN : 256);
+  constexpr int ACC_COLS = P * BN * (NC ? 2 : 1);            // TMEM columns of one accumulator set
+  constexpr int NSETS = (2 * ACC_COLS <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = NSETS * ACC_COLS <= 32 ? 32 : NSETS * ACC_COLS <= 64 ? 64 : NSETS * ACC_COLS <= 128 ? 128 : NSETS * ACC_COLS <= 256 ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,7 +112,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   // [halo stage 0: hi | lo][halo stage 1: hi | lo][B ring: BST x (hi | lo)][barriers]
   constexpr int HALO_BYTES = 2 * HL_PLANE;
   constexpr int B_OFF = HL_HALO_STAGES * HALO_BYTES;
-  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * STAGE_B);            // [2 slots][mul | add | prelu][BN]
+  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * STAGE_B);            // [2 slots][mul | add | slope][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * STAGE_B + 2 * 3 * BN * 4);
   const uint32_t bar_hfull = smem_u32(bars);                 // 2
   const uint32_t bar_hempty = bar_hfull + 16;                // 2
@@ -91,27 +121,36 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   const uint32_t bar_afull = bar_bempty + 8 * HL_MAX_BST;    // 2
   const uint32_t bar_aempty = bar_afull + 16;                // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * HL_MAX_BST);
+  long long* s_acct = reinterpret_cast<long long*>(bars + 24);                     // [4 roles][8 laps]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P = up ? 4 : 1;
-  const int PL = P / PM;                                      // MMA groups of PM merged phases
+  const int dbg = g_hl_dbg;                                  // read ONCE (a global load per use otherwise)
+  const bool acct = g_hl_trace != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 8 * 32 || tid == HL_MMA_WARP * 32 || tid == (HL_MMA_WARP + 1) * 32);
+  long long acct_t = 0;
   const int cin_eff = p.cin < 64 ? p.cin : 64;               // channels per halo row actually used
   const int G = p.cin < 64 ? 1 : p.cin / 64;                 // 64-channel groups
   const int ksteps = cin_eff / 16;
   const int tpc = 64 / cin_eff;                              // taps per packed 64-wide K chunk (1, or 2 when cin == 32)
   const int CPG = (9 + tpc - 1) / tpc;                       // packed chunks per (phase, group)
   const int num_kc = (9 * p.cin + 63) / 64;
-  const int nsets = (2 * P * BN <= 512) ? 2 : 1;
   // masked layers: one job per (tile, region present in the tile) from a device-built list (e4s_region_tile_jobs);
   // the halo is modulated with that region's style and the epilogue keeps only the rows that belong to the region
   const int total_jobs = rjobs ? __ldg(rjob_count) * n_tiles : total_jobs_in;
   const int my_jobs = total_jobs > (int)blockIdx.x ? (total_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // every weight chunk of a job fits the ring and all jobs use the same tiles: load once, keep resident
+  const bool resident = n_tiles == 1 && G * PL * CPG <= BST;
+  const bool pow2 = ((tiles_x & (tiles_x - 1)) | (tiles_y & (tiles_y - 1))) == 0;
+  const int sx_sh = 31 - __clz(tiles_x), sy_sh = 31 - __clz(tiles_y);
 
   auto decode = [&](int it) {
     int j = (int)blockIdx.x + it * (int)gridDim.x;
     HlJob r;
-    r.nt = j % n_tiles;
-    j /= n_tiles;
+    if (n_tiles == 1) {
+      r.nt = 0;
+    } else {
+      r.nt = j % n_tiles;
+      j /= n_tiles;
+    }
     if (rjobs) {
       const int4 jv = __ldg(rjobs + j);
       r.b = jv.x;
@@ -121,12 +160,11 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       return r;
     }
     r.reg = 0;
-    if (((tiles_x & (tiles_x - 1)) | (tiles_y & (tiles_y - 1))) == 0) {   // power-of-two grids: shifts instead of divisions
-      const int sx = 31 - __clz(tiles_x), sy = 31 - __clz(tiles_y);
+    if (pow2) {                                              // power-of-two grids: shifts instead of divisions
       r.x0 = (j & (tiles_x - 1)) * HL_TW;
-      j >>= sx;
+      j >>= sx_sh;
       r.y0 = (j & (tiles_y - 1)) * HL_TH;
-      r.b = j >> sy;
+      r.b = j >> sy_sh;
       return r;
     }
     r.x0 = (j % tiles_x) * HL_TW;
@@ -136,6 +174,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     return r;
   };
 
+  if (tid < 32) s_acct[tid] = 0;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_hfull + 8 * s, TC_PRODUCER_WARPS);
@@ -150,30 +189,34 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(nsets * P * BN)) tmem_cols <<= 1;
-  if (warp == HL_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  if (warp == HL_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (acct) acct_t = clock64();
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================== halo producers ===================================================
-    const int cg = tid & 7;
-    const int px0 = tid >> 3;                                // halo pixels px0, px0+32, ...
-    const bool cg_live = cg * 8 < cin_eff;
+    const int cgs = cin_eff == 32 ? 2 : 3;                   // lanes per pixel = cin_eff / 8 (4 or 8)
+    const int cg = tid & ((1 << cgs) - 1);
+    const int px0 = tid >> cgs;                              // halo pixels px0, px0 + pxs, ...
+    const int pxs = 256 >> cgs;
     const int total_hg = my_jobs * G;                        // halo fills this CTA performs
 
     float4 v[HL_ITEMS][2];
     uint32_t okm = 0;
     float4 sc[2], mn[2], rs[2];                              // per-(sample, channel) modulation / InstanceNorm of this fill
-    auto prefetch = [&](int hg) {
+    int pit = 0, pg = 0;                                     // (job, channel group) of the next prefetch
+    auto prefetch = [&]() {
       okm = 0;
-      if (hg >= total_hg || !cg_live) return;
-      const int it = hg / G, g = hg - it * G;
-      const HlJob jb = decode(it);
-      const int ch = g * 64 + cg * 8;
+      if (pit >= my_jobs) return;
+      const HlJob jb = decode(pit);
+      const int ch = pg * 64 + cg * 8;
+      if (++pg == G) {
+        pg = 0;
+        ++pit;
+      }
       if (p.smod) {
         const float4* sp = reinterpret_cast<const float4*>(p.smod + ((int64_t)jb.b * p.regions + jb.reg) * p.cin + ch);
         sc[0] = __ldg(sp);
@@ -185,33 +228,33 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         mn[0] = __ldg(mp); mn[1] = __ldg(mp + 1);
         rs[0] = __ldg(qp); rs[1] = __ldg(qp + 1);
       }
+      const float* xb = p.x + (int64_t)jb.b * p.hin * p.win * p.x_pitch + ch;
 #pragma unroll
       for (int i = 0; i < HL_ITEMS; ++i) {
-        const int px = px0 + 32 * i;
+        const int px = px0 + pxs * i;
         const int hy = px / HL_HP, hx = px - hy * HL_HP;
         const int iy = jb.y0 - 1 + hy, ix = jb.x0 - 1 + hx;
         if (px < HL_HPIX && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
           okm |= 1u << i;
-          const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)jb.b * p.hin + iy) * p.win + ix) * p.x_pitch + ch);
+          const float4* src = reinterpret_cast<const float4*>(xb + (int64_t)(iy * p.win + ix) * p.x_pitch);
           v[i][0] = ldg_stream4(src);
           v[i][1] = ldg_stream4(src + 1);
         }
       }
     };
 
-    const int pdbg = g_hl_dbg;
-    if (!(pdbg & 32)) prefetch(0);
+    if (!(dbg & 32)) prefetch();
     for (int hg = 0; hg < total_hg; ++hg) {
       const int hs = hg & 1;
-      if (tid == 0) hl_trace(0, hg, 0);
+      HL_LAP(0, 0);
       mbar_wait(bar_hempty + 8 * hs, ((hg >> 1) & 1) ^ 1);
-      if (tid == 0) hl_trace(0, hg, 1);
+      HL_LAP(0, 1);
       uint8_t* h_hi = smem + hs * HALO_BYTES;
       uint8_t* h_lo = h_hi + HL_PLANE;
-      if (cg_live && !(pdbg & 32)) {
+      if (!(dbg & 32)) {
 #pragma unroll
         for (int i = 0; i < HL_ITEMS; ++i) {
-          const int px = px0 + 32 * i;
+          const int px = px0 + pxs * i;
           if (px >= HL_HPIX) continue;
           float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (okm & (1u << i)) {
@@ -242,168 +285,254 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           *reinterpret_cast<uint4*>(h_lo + off_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
-      if (tid == 0) hl_trace(0, hg, 2);
+      HL_LAP(0, 2);
       // publish the halo FIRST: fence.proxy.async waits for this thread's outstanding memory operations, so issuing the
       // next job's global loads before it would serialise their full DRAM latency into every job
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfull + 8 * hs);
-      if (!(pdbg & 32)) prefetch(hg + 1);
-      if (tid == 0) hl_trace(0, hg, 3);
+      HL_LAP(0, 3);
+      if (!(dbg & 32)) prefetch();
+      HL_LAP(0, 4);
     }
   } else if (warp < HL_MMA_WARP) {
     // =========================== epilogue warpgroup ===============================================
+    // Software pipeline: the job descriptor is decoded two jobs ahead and the per-pixel operands (noise, float mask,
+    // region label) are LOADED one job ahead and left untouched in registers until their job (any arithmetic on them
+    // right after the load would stall this warp for the full L2 latency).  The fused per-channel vectors in shared
+    // memory are rebuilt only when (sample, region, n-tile) changes.
     const int q = warp & 3;
     const int row = q * 32 + lane;                           // GEMM row = ty*8 + tx
     const int ty = row >> 3, tx = row & 7;
     const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
-    const int dbg = g_hl_dbg;
-    for (int it = 0; it < my_jobs; ++it) {
-      const HlJob jb = decode(it);
-      const int set = nsets == 2 ? (it & 1) : 0;
-      const int use = nsets == 2 ? (it >> 1) : it;
-      // per-pixel epilogue operands (noise / float-mask loads) are fetched BEFORE waiting for the accumulator
-      const float* drow = p.demod ? p.demod + ((int64_t)jb.b * p.regions + jb.reg) * p.cout : nullptr;
-      TcEpiRow er[4];
-      uint32_t rowlive = 0xf;                                   // per phase: does this row (pixel) belong to the job's region
+    const bool need_lab = rjobs != nullptr;
+    const bool noise1 = p.noise && p.noise_sc == 0;
+    const bool fast = tc_epi_is_fast(p) && !(dbg & (1 | 2 | 8 | 16 | 128));    // bit7: force the generic epilogue
+    const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
+
+    struct RowOps {
+      float nz[P], pw[P];
+      uint32_t lab[P];
+    };
+    auto fetch_rows = [&](const HlJob& j, RowOps& o) {
 #pragma unroll
-      for (int ph = 0; ph < 4; ++ph) {
-        if (ph >= P) break;
-        const int oy = up ? 2 * (jb.y0 + ty) + (ph >> 1) : jb.y0 + ty;
-        const int ox = up ? 2 * (jb.x0 + tx) + (ph & 1) : jb.x0 + tx;
-        er[ph].pix = ((int64_t)jb.b * p.hout + oy) * p.wout + ox;
-        if (rjobs) {
+      for (int ph = 0; ph < P; ++ph) {
+        o.nz[ph] = 0.f;
+        o.pw[ph] = 1.f;
+        o.lab[ph] = 0;
+        const int oy = UP ? 2 * (j.y0 + ty) + (ph >> 1) : j.y0 + ty;
+        const int ox = UP ? 2 * (j.x0 + tx) + (ph & 1) : j.x0 + tx;
+        if (need_lab || p.pixw) {
           const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
-          if (p.labels[((int64_t)jb.b * p.lab_h + sy) * p.lab_w + sx] != jb.reg) rowlive &= ~(1u << ph);
+          if (need_lab) o.lab[ph] = p.labels[((int64_t)j.b * p.lab_h + sy) * p.lab_w + sx];
+          if (p.pixw) o.pw[ph] = __ldg(p.pixw + (int64_t)j.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
         }
-        er[ph].drow = drow;
-        er[ph].pw = 1.f;
-        if (p.pixw) {
-          const int sy = nearest_src(oy, p.lab_h, p.hout), sx = nearest_src(ox, p.lab_w, p.wout);
-          er[ph].pw = __ldg(p.pixw + (int64_t)jb.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
+        if (noise1) o.nz[ph] = __ldg(p.noise + (int64_t)j.b * p.noise_sb + (int64_t)oy * p.wout + ox);
+      }
+    };
+
+    HlJob jb = decode(0), jb1 = decode(my_jobs > 1 ? 1 : 0);
+    RowOps cur, nxt;
+    if (my_jobs > 0) fetch_rows(jb, cur);
+    nxt = cur;
+    int kb = -1, knt = -1, kreg = -1, slot = 0;
+    for (int it = 0; it < my_jobs; ++it) {
+      const int set = NSETS == 2 ? (it & 1) : 0;
+      const int use = NSETS == 2 ? (it >> 1) : it;
+      const HlJob jb2 = decode(it + 2 < my_jobs ? it + 2 : it);
+      if (it + 1 < my_jobs) fetch_rows(jb1, nxt);
+      const float* drow = p.demod ? p.demod + ((int64_t)jb.b * p.regions + jb.reg) * p.cout : nullptr;
+      const int oy0 = UP ? 2 * (jb.y0 + ty) : jb.y0 + ty, ox0 = UP ? 2 * (jb.x0 + tx) : jb.x0 + tx;
+      const int64_t pix0 = ((int64_t)jb.b * p.hout + oy0) * p.wout + ox0;
+      HL_LAP(1, 0);
+      if (jb.b != kb || jb.nt != knt || jb.reg != kreg) {
+        // fused per-channel vectors of this (sample, region, n-tile) -> the other shared-memory slot.  Every warp has left
+        // the jobs that read that slot before it passed the previous rebuild's barrier.
+        kb = jb.b; knt = jb.nt; kreg = jb.reg;
+        slot ^= 1;
+        float* svw = s_epi + slot * 3 * BN;
+        for (int n = tid - 8 * 32; n < BN; n += 128) {
+          const int ng = jb.nt * BN + n;
+          float mul = drow ? __ldg(drow + ng) : 1.f;
+          if (p.ch_scale) mul *= __ldg(p.ch_scale + ng);
+          svw[n] = mul;
+          svw[BN + n] = p.ch_shift ? __ldg(p.ch_shift + ng) : 0.f;
+          svw[2 * BN + n] = tc_epi_slope(p, ng);
         }
-        er[ph].nw = nw;
-        er[ph].nrow = p.noise ? p.noise + (int64_t)jb.b * p.noise_sb + (int64_t)oy * p.wout + ox : nullptr;
-        er[ph].nz = (er[ph].nrow && p.noise_sc == 0) ? nw * __ldg(er[ph].nrow) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
       }
-      if (warp == 8 && lane == 0) hl_trace(1, it, 0);
-      // fused per-channel vectors of this job -> shared memory (demod is per sample; everything else per layer)
-      float* sv = s_epi + (it & 1) * 3 * BN;
-      for (int n = tid - 8 * 32; n < BN; n += 128) {
-        const int ng = jb.nt * BN + n;
-        float mul = drow ? __ldg(drow + ng) : 1.f;
-        if (p.ch_scale) mul *= __ldg(p.ch_scale + ng);
-        sv[n] = mul;
-        sv[BN + n] = p.ch_shift ? __ldg(p.ch_shift + ng) : 0.f;
-        sv[2 * BN + n] = p.act == E4S_ACT_PRELU ? __ldg(p.act_prelu + ng) : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
+      const float* sv = s_epi + slot * 3 * BN;
+      HL_LAP(1, 3);
       mbar_wait(bar_afull + 8 * set, use & 1);
       tc_fence_after();
-      if (warp == 8 && lane == 0) hl_trace(1, it, 1);
+      HL_LAP(1, 1);
 #pragma unroll
-      for (int ph = 0; ph < 4; ++ph) {
-        if (ph >= P) break;
-        const uint32_t tacc = tmem_base + (uint32_t)((set * P + ph) * BN) + ((uint32_t)(q * 32) << 16);
+      for (int ph = 0; ph < P; ++ph) {
+        const uint32_t tacc = tmem_base + (uint32_t)(set * ACC_COLS + ph * BN) + ((uint32_t)(q * 32) << 16);
+        const int64_t pix = UP ? pix0 + (ph >> 1) * p.wout + (ph & 1) : pix0;
+        const bool live = !need_lab || cur.lab[ph] == (uint32_t)jb.reg;
+        if (fast) {
+          float* optr = p.out + pix * p.out_pitch + jb.nt * BN;
+          const float nz = nw * cur.nz[ph];
+          if (NC) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+              uint32_t ra[16], rb[16];
+              float acc[16];
+              tmem_ld16_nowait(tacc + (uint32_t)c0, ra);
+              tmem_ld16_nowait(tacc + (uint32_t)(BN + c0), rb);
+              tmem_wait_ld16x2(ra, rb);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+              if (live) tc_epilogue_fast<16>(optr + c0, acc, sv, c0, BN, nz, gain);
+            }
+          } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+              uint32_t ra[32];
+              float acc[32];
+              tmem_ld32_nowait(tacc + (uint32_t)c0, ra);
+              tmem_wait_ld32(ra);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(ra[j]);
+              if (live) tc_epilogue_fast<32>(optr + c0, acc, sv, c0, BN, nz, gain);
+            }
+          }
+          continue;
+        }
+        TcEpiRow er;
+        er.pix = pix;
+        er.drow = drow;
+        er.pw = cur.pw[ph];
+        er.nw = nw;
+        er.nrow = p.noise ? p.noise + (int64_t)jb.b * p.noise_sb + (int64_t)(UP ? oy0 + (ph >> 1) : oy0) * p.wout + (UP ? ox0 + (ph & 1) : ox0) : nullptr;
+        er.nz = nw * cur.nz[ph];
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float acc[16];
           if (!(dbg & 2)) {
             tmem_ld16(tacc + (uint32_t)c0, acc);
+            if (NC) {
+              float acc2[16];
+              tmem_ld16(tacc + (uint32_t)(BN + c0), acc2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] += acc2[j];
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.f;
           }
-          if (!(dbg & 1) && (rowlive & (1u << ph))) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er[ph], dbg);
+          if (!(dbg & 1) && live) tc_epilogue16_sv(p, acc, jb.nt * BN + c0, c0, BN, sv, er, dbg);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_aempty + 8 * set);
-      if (warp == 8 && lane == 0) hl_trace(1, it, 2);
+      HL_LAP(1, 2);
+      jb = jb1;
+      jb1 = jb2;
+      cur = nxt;
     }
   } else if (warp == HL_MMA_WARP) {
     // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ==
-    {
-      int hg = 0, bc = 0;                                    // running halo-fill and weight-chunk counters
-      for (int it = 0; it < my_jobs; ++it) {
-        const int set = nsets == 2 ? (it & 1) : 0;
-        const int use = nsets == 2 ? (it >> 1) : it;
-        if (lane == 0) hl_trace(2, it, 0);
-        mbar_wait(bar_aempty + 8 * set, (use & 1) ^ 1);
+    constexpr uint32_t A_HI = umma_desc_hi(HL_HP * 128), B_HI = umma_desc_hi(1024);
+    const uint32_t kb16 = (uint32_t)(cin_eff * 2) >> 4;     // 16-byte units per tap inside a packed 64-wide K chunk
+    int hg = 0, bs = 0, bph = 0;                             // running halo-fill counter, weight stage and its phase parity
+    for (int it = 0; it < my_jobs; ++it) {
+      if (resident) bs = 0;                                  // resident weights: chunk i of every job lives in stage i
+      const int set = NSETS == 2 ? (it & 1) : 0;
+      const int use = NSETS == 2 ? (it >> 1) : it;
+      HL_LAP(2, 0);
+      mbar_wait(bar_aempty + 8 * set, (use & 1) ^ 1);
+      tc_fence_after();
+      HL_LAP(2, 1);
+      for (int g = 0; g < G; ++g, ++hg) {
+        const int hs = hg & 1;
+        mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
+        HL_LAP(2, 2);
         tc_fence_after();
-        if (lane == 0) hl_trace(2, it, 1);
-        for (int g = 0; g < G; ++g, ++hg) {
-          const int hs = hg & 1;
-          mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
-          if (lane == 0) hl_trace(2, it, 2);
-          tc_fence_after();
-          const uint32_t h_hi = smem_base + hs * HALO_BYTES;
-          // descriptors are affine in the byte address: desc(a + off) = desc(a) + (off >> 4)  (14-bit field, smem < 256 KB)
-          const uint64_t dah0 = umma_smem_desc_sbo(h_hi, HL_HP * 128), dal0 = umma_smem_desc_sbo(h_hi + HL_PLANE, HL_HP * 128);
-          for (int pl = 0; pl < PL; ++pl) {
-            const uint32_t tacc = tmem_base + (uint32_t)((set * P + pl * PM) * BN);
-            for (int c = 0; c < CPG; ++c, ++bc) {
-              const int bs = bc % BST;
-              mbar_wait(bar_bfull + 8 * bs, (bc / BST) & 1);
+        const uint32_t a_h = umma_desc_lo(smem_base + hs * HALO_BYTES), a_l = umma_desc_lo(smem_base + hs * HALO_BYTES + HL_PLANE);
+#pragma unroll
+        for (int pl = 0; pl < PL; ++pl) {
+          const uint32_t tacc = tmem_base + (uint32_t)(set * ACC_COLS + pl * PM * BN);
+          int tap = 0;
+          for (int c = 0; c < CPG; ++c) {
+            HL_LAP(2, 5);
+            if (!resident || it == 0) {
+              mbar_wait(bar_bfull + 8 * bs, bph);
               tc_fence_after();
-              const uint32_t b_hi = smem_base + B_OFF + bs * STAGE_B;
-              const uint64_t dbh0 = umma_smem_desc(b_hi), dbl0 = umma_smem_desc(b_hi + PM * B_BYTES);
-              if (elect_one()) {
-                for (int tt = 0; tt < ((g_hl_dbg & 4) ? 0 : tpc); ++tt) {
-                  const int tap = c * tpc + tt;
-                  if (tap >= 9) break;
-                  const uint32_t aoff = ((uint32_t)((tap / 3) * HL_HP + (tap % 3)) * 128u) >> 4;
-                  const uint32_t boff = (uint32_t)(tt * cin_eff * 2) >> 4;
+            }
+            HL_LAP(2, 4);
+            const uint32_t b_h = umma_desc_lo(smem_base + B_OFF + bs * STAGE_B), b_l = b_h + ((PM * B_BYTES) >> 4);
+            if (elect_one()) {
+              if (!(dbg & 4)) {
+                uint32_t boff = 0;
+                for (int tt = 0; tt < tpc && tap + tt < 9; ++tt, boff += kb16) {
+                  const int t9 = tap + tt;
+                  const uint32_t aoff = (uint32_t)((t9 / 3) * HL_HP + (t9 % 3)) * 8u;
                   for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t dah = dah0 + aoff + 2 * k, dal = dal0 + aoff + 2 * k;
-                    const uint64_t dbh = dbh0 + boff + 2 * k, dbl = dbl0 + boff + 2 * k;
-                    umma_bf16(tacc, dal, dbh, IDESC, (g | tap | k) != 0);
-                    umma_bf16(tacc, dah, dbl, IDESC, 1);
-                    umma_bf16(tacc, dah, dbh, IDESC, 1);
+                    const uint32_t ao = aoff + 2 * k, bo = boff + 2 * k;
+                    const uint32_t first = (uint32_t)((g | t9 | k) != 0);
+                    if (NC) {
+                      umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC2, first);   // A_hi x [B_hi ; B_lo] -> both accumulator halves
+                      umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, 1);        // A_lo x B_hi        -> first half
+                    } else {
+                      umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, first);
+                      umma_bf16_w(tacc, a_h + ao, A_HI, b_l + bo, B_HI, IDESC, 1);
+                      umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC, 1);
+                    }
                   }
                 }
-                umma_commit(bar_bempty + 8 * bs);
               }
-              __syncwarp();
+              if (!resident) umma_commit(bar_bempty + 8 * bs);
+            }
+            __syncwarp();
+            tap += tpc;
+            if (++bs == BST) {
+              bs = 0;
+              bph ^= 1;
             }
           }
-          if (elect_one()) umma_commit(bar_hempty + 8 * hs);  // every tap of every phase has read this halo
-          __syncwarp();
         }
-        if (elect_one()) umma_commit(bar_afull + 8 * set);
+        if (elect_one()) umma_commit(bar_hempty + 8 * hs);    // every tap of every phase has read this halo
         __syncwarp();
-        if (lane == 0) hl_trace(2, it, 3);
       }
+      if (elect_one()) umma_commit(bar_afull + 8 * set);
+      __syncwarp();
+      HL_LAP(2, 3);
     }
     __syncwarp();
   } else {
     // =========================== weight loader ====================================================
-    {
-      const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
-      int bc = 0;
-      for (int it = 0; it < my_jobs; ++it) {
-        const HlJob jb = decode(it);
-        for (int g = 0; g < G; ++g)
-          for (int pl = 0; pl < PL; ++pl)
-            for (int c = 0; c < CPG; ++c, ++bc) {
-              const int bs = bc % BST;
-              const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
-              mbar_wait(bar_bempty + 8 * bs, ((bc / BST) & 1) ^ 1);
-              if (g_hl_dbg & 64) {
-                if (elect_one()) mbar_arrive(bar_bfull + 8 * bs);
-              } else if (elect_one()) {
-                const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
-                mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
-                for (int q = 0; q < PM; ++q) {               // hi tiles of the merged phases back to back, then the lo tiles
-                  const uint8_t* src = wpk + (((int64_t)(pl * PM + q) * n_tiles + jb.nt) * num_kc + kc) * tile_bytes;
-                  bulk_g2s(dst + q * B_BYTES, src, B_BYTES, bar_bfull + 8 * bs);
-                  bulk_g2s(dst + (PM + q) * B_BYTES, src + B_BYTES, B_BYTES, bar_bfull + 8 * bs);
-                }
+    const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
+    int bs = 0, bph = 0;
+    for (int it = 0; it < (resident ? (my_jobs > 0 ? 1 : 0) : my_jobs); ++it) {
+      const HlJob jb = decode(it);
+      for (int g = 0; g < G; ++g)
+        for (int pl = 0; pl < PL; ++pl)
+          for (int c = 0; c < CPG; ++c) {
+            const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
+            HL_LAP(3, 1);
+            mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+            HL_LAP(3, 0);
+            if (dbg & 64) {
+              if (elect_one()) mbar_arrive(bar_bfull + 8 * bs);
+            } else if (elect_one()) {
+              const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
+              mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
+#pragma unroll
+              for (int q = 0; q < PM; ++q) {               // hi tiles of the merged phases back to back, then the lo tiles
+                const uint8_t* src = wpk + (((int64_t)(pl * PM + q) * n_tiles + jb.nt) * num_kc + kc) * tile_bytes;
+                bulk_g2s(dst + q * B_BYTES, src, B_BYTES, bar_bfull + 8 * bs);
+                bulk_g2s(dst + (PM + q) * B_BYTES, src + B_BYTES, B_BYTES, bar_bfull + 8 * bs);
               }
-              __syncwarp();
             }
-      }
+            __syncwarp();
+            if (++bs == BST) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
     }
     __syncwarp();
   }
@@ -412,8 +541,10 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   __syncthreads();
   if (warp == HL_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (g_hl_trace != nullptr && blockIdx.x == 0 && tid < 32 && tid < g_hl_trace_cap) g_hl_trace[tid] = (unsigned long long)s_acct[tid];
+  if (g_hl_trace != nullptr && blockIdx.x == 0 && tid == 32 && 32 < g_hl_trace_cap) g_hl_trace[32] = (unsigned long long)my_jobs;
 }
 
 // One CTA per 16x8 tile: which regions own at least one of the tile's output pixels?  Appends one int4 job
@@ -472,14 +603,14 @@ bool tc_halo_eligible(const E4SConv* p) {
   return tc_halo_geometry_ok(p);
 }
 
-template <int BN>
+template <int BN, bool UP>
 static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs = nullptr, const int* rjob_count = nullptr,
                        int rjob_host_count = 0) {
   static bool attr_set = false;
-  const int pm = hl_phase_merge(BN, p->mode == E4S_CONV_UP2_POLYPHASE);
-  const int smem_bytes = hl_smem_bytes(BN, pm);
+  constexpr int pm = hl_phase_merge(BN, UP);
+  constexpr int smem_bytes = hl_smem_bytes(BN, pm);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX);
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -493,7 +624,7 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
   const int64_t total = rjobs ? (int64_t)rjob_host_count * n_tiles : (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
   E4S_REQUIRE(total > 0 && total < 0x7fffffff, "conv_tc(halo): bad job count");
   const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
-  conv_tc_halo_kernel<BN><<<grid, HL_THREADS, smem_bytes, s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
+  conv_tc_halo_kernel<BN, UP><<<grid, HL_THREADS, smem_bytes, s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
                                                                      (int)total, rjobs, rjob_count);
   return check_launch("e4s_conv_tc(halo)");
 }
@@ -505,19 +636,18 @@ int tc_halo_set_flags(int flags) {
 
 int tc_halo_set_trace(void* buf, int cap_records) {
   unsigned long long* ptr = static_cast<unsigned long long*>(buf);
-  int zero = 0;
   cudaError_t e = cudaMemcpyToSymbol(g_hl_trace, &ptr, sizeof(ptr));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_hl_trace_cap, &cap_records, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_hl_trace_n, &zero, sizeof(int));
   return e == cudaSuccess ? E4S_OK : fail(E4S_ERR_CUDA, "halo trace: %s", cudaGetErrorString(e));
 }
 
 int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs, const int* rjob_count, int rjob_host_count) {
+  const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   switch (tc_block_n(p->cout)) {
-    case 256: return launch_halo<256>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
-    case 128: return launch_halo<128>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
-    case 64: return launch_halo<64>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
-    case 32: return launch_halo<32>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 256: return launch_halo<256, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);     // up: 4 x 256 columns exceed TMEM (geometry_ok)
+    case 128: return up ? launch_halo<128, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<128, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 64: return up ? launch_halo<64, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<64, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 32: return up ? launch_halo<32, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<32, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
     default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc(halo): unsupported cout %d", p->cout);
   }
 }

@@ -103,6 +103,45 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive accumulator columns of this thread's TMEM lane, no wait (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// the registers are threaded through the wait as in/out operands so that no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld16x2(uint32_t (&r)[16], uint32_t (&q)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(q[0]), "+r"(q[1]), "+r"(q[2]),
+                 "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]),
+                 "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+               :
+               : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  Field layout: cute/arch/mma_sm100_desc.hpp.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
@@ -258,6 +297,35 @@ __device__ __forceinline__ void tc_epilogue16_sv(const E4SConv& p, const float (
       a = tc_epi_math4(p, a, r, n0 + 4 * q, mul, add, pre);
     }
     if (!(dbg & 8) || a.x == 123456.789f) tc_epi_store4(p, o + q, a);
+  }
+}
+
+// Fast epilogue (chosen once per kernel, outside every loop): no residual / float mask / accumulate / per-channel noise and an
+// activation of the piecewise-linear family.  sv = [mul | add | negative-side slope] per channel; NONE, ReLU, leaky ReLU
+// and PReLU all are  t = acc*mul + (add + nz);  out = (t < 0 ? t*slope : t) * gain  -- no branches, no constant-bank
+// loads per element (the generic path spends ~70 instructions per float4 on uniform branches).
+__host__ __device__ __forceinline__ bool tc_epi_is_fast(const E4SConv& p) {
+  return !p.res && !p.pixw && !p.accumulate && (!p.noise || p.noise_sc == 0) &&
+         (p.act == E4S_ACT_NONE || p.act == E4S_ACT_RELU || p.act == E4S_ACT_LRELU || p.act == E4S_ACT_PRELU);
+}
+__device__ __forceinline__ float tc_epi_slope(const E4SConv& p, const int n) {
+  return p.act == E4S_ACT_PRELU ? __ldg(p.act_prelu + n) : (p.act == E4S_ACT_LRELU ? p.act_slope : (p.act == E4S_ACT_RELU ? 0.f : 1.f));
+}
+template <int NV>   // NV consecutive channels (multiple of 4) of one pixel
+__device__ __forceinline__ void tc_epilogue_fast(float* __restrict__ optr, const float (&acc)[NV], const float* sv, const int nl, const int bn,
+                                                 const float nz, const float gain) {
+  float4* o = reinterpret_cast<float4*>(optr);
+#pragma unroll
+  for (int q = 0; q < NV / 4; ++q) {
+    const float4 mul = *reinterpret_cast<const float4*>(sv + nl + 4 * q);
+    const float4 add = *reinterpret_cast<const float4*>(sv + bn + nl + 4 * q);
+    const float4 sl = *reinterpret_cast<const float4*>(sv + 2 * bn + nl + 4 * q);
+    float4 a;
+    a.x = fmaf(acc[4 * q], mul.x, add.x + nz); a.y = fmaf(acc[4 * q + 1], mul.y, add.y + nz);
+    a.z = fmaf(acc[4 * q + 2], mul.z, add.z + nz); a.w = fmaf(acc[4 * q + 3], mul.w, add.w + nz);
+    a.x = (a.x < 0.f ? a.x * sl.x : a.x) * gain; a.y = (a.y < 0.f ? a.y * sl.y : a.y) * gain;
+    a.z = (a.z < 0.f ? a.z * sl.z : a.z) * gain; a.w = (a.w < 0.f ? a.w * sl.w : a.w) * gain;
+    o[q] = a;
   }
 }
 

@@ -26,33 +26,23 @@ for flags in (0, 1, 8, 16, 24, 7):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); E.conv(E.View(x), pw, engine="tc", out=out, **kw); e1.record(); torch.cuda.synchronize()
     print(f"flags {flags}: kernel {e0.elapsed_time(e1):.3f} ms (no trace)")
-L.lib().e4s_debug_halo_flags(0)
-cap = 40000
-buf = torch.zeros(2 * cap, dtype=torch.int64, device="cuda")
-L.lib().e4s_debug_halo_trace(C.c_void_p(buf.data_ptr()), cap)
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); E.conv(E.View(x), pw, engine="tc", out=out, **kw); e1.record()
-torch.cuda.synchronize()
-L.lib().e4s_debug_halo_trace(None, 0)
-print("kernel ms", e0.elapsed_time(e1))
-rec = buf.cpu().numpy().reshape(-1, 2)
-rec = rec[rec[:, 1] != 0]
-role = rec[:, 0] >> 48; it = (rec[:, 0] >> 16) & 0xffffff; ev = rec[:, 0] & 0xffff; t = rec[:, 1] - rec[:, 1].min()
-names = {0: "producer", 1: "epilogue", 2: "mma"}
-for r in (0, 1, 2):
-    m = role == r
-    print(f"--- {names[r]}: {m.sum()} records")
-    evs = sorted(set(ev[m]))
-    # mean duration between consecutive events within a job, and job period
-    per = {}
-    for e in evs:
-        tt = t[m & (ev == e)]; ii = it[m & (ev == e)]
-        order = np.argsort(ii); per[e] = (ii[order], tt[order])
-    base = per[evs[0]]
-    n = min(len(v[0]) for v in per.values())
-    ref = per[evs[0]][1][:n]
-    for e in evs[1:]:
-        d = per[e][1][:n] - ref
-        print(f"  ev{evs[0]}->ev{e}: mean {d[5:].mean():9.0f} cyc  (p50 {np.median(d[5:]):9.0f})")
-    period = np.diff(base[1][:n])
-    print(f"  job period: mean {period[5:].mean():9.0f} cyc over {n} jobs")
+cap = 64
+LAPS = {0: ("producer", {0: "loop", 1: "wait hempty", 2: "convert+st.shared", 3: "fence+arrive", 4: "prefetch issue"}),
+        1: ("epilogue", {0: "job setup", 3: "sv rebuild", 1: "wait afull", 2: "tmem ld + math + stores + arrive"}),
+        2: ("mma", {0: "loop", 1: "wait aempty", 2: "wait hfull", 4: "wait bfull", 5: "issue (chunks)", 3: "issue (last chunk) + commits"}),
+        3: ("loader", {0: "wait bempty", 1: "issue"})}
+for flags in [int(f) for f in os.environ.get("TRACE_FLAGS", "0").split(",")]:
+    L.lib().e4s_debug_halo_flags(flags)
+    buf = torch.zeros(cap, dtype=torch.int64, device="cuda")
+    L.lib().e4s_debug_halo_trace(C.c_void_p(buf.data_ptr()), cap)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); E.conv(E.View(x), pw, engine="tc", out=out, **kw); e1.record()
+    torch.cuda.synchronize()
+    L.lib().e4s_debug_halo_trace(None, 0)
+    L.lib().e4s_debug_halo_flags(0)
+    v = buf.cpu().numpy()
+    jobs = max(int(v[32]), 1)
+    print(f"=== flags {flags}: kernel {e0.elapsed_time(e1):.3f} ms with accounting, CTA 0 ran {jobs} jobs; cycles per job:")
+    for r, (name, laps) in LAPS.items():
+        tot = sum(v[r * 8 + k] for k in laps) / jobs
+        print(f"  {name:9s} total {tot:8.0f} | " + " | ".join(f"{n} {v[r * 8 + k] / jobs:.0f}" for k, n in laps.items()))
