@@ -142,6 +142,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     const int ntaps = p.kh * p.kw;
     const bool grouped = (p.cin % 64) == 0;
 
+    // Grouped K order: the taps of one 64-channel group run back to back, so the per-row modulation / InstanceNorm vectors
+    // of this thread's 8 channels change only every `ntaps` chunks: keep them in registers instead of re-reading them
+    // (2 extra 16-byte loads per row and chunk, with their L1 latency exposed right before the conversion).  The
+    // InstanceNorm vectors (encoder only) stay as loads: caching them too costs 64 registers and spills.
+    float4 sreg[4][2];
+    int cached_g = -1;
     float4 v[4][2];
     bool ok[4];
     auto prefetch = [&](int kc) {
@@ -183,6 +189,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       uint8_t* a_hi = smem + s * STAGE_BYTES;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
       const int ci = grouped ? (kc / ntaps) * 64 + cg * 8 : (kc * TC_BK + cg * 8) % p.cin;
+      const int gcur = grouped ? kc / ntaps : kc;
+      if (gcur != cached_g) {
+        cached_g = gcur;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (rs[i]) {
+            sreg[i][0] = __ldg(reinterpret_cast<const float4*>(rs[i] + ci)); sreg[i][1] = __ldg(reinterpret_cast<const float4*>(rs[i] + ci) + 1);
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = r0 + 32 * i;
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
             f[4] = (f[4] - m1.x) * q1.x; f[5] = (f[5] - m1.y) * q1.y; f[6] = (f[6] - m1.z) * q1.z; f[7] = (f[7] - m1.w) * q1.w;
           }
           if (rs[i]) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(rs[i] + ci)), s1 = __ldg(reinterpret_cast<const float4*>(rs[i] + ci) + 1);
+            const float4 s0 = sreg[i][0], s1 = sreg[i][1];
             f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
             f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
           }
@@ -245,11 +261,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     er.nw = p.noise ? __ldg(p.noise_w) : 0.f;
     er.nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
     er.nz = (er.nrow && p.noise_sc == 0) ? er.nw * __ldg(er.nrow) : 0.f;
+    if (tc_epi_is_fast(p)) {
+      // branch-free epilogue (tc_ptx.cuh): per-row demodulation from global memory (rows of a tile may belong to different
+      // regions), the layer-wide bias / slope vectors through a 16-column register block
+      const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
+      const float nz = er.nz;
+      float* optr = p.out + pix * p.out_pitch + n_base;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN / 2; c0 += 16) {
-      float acc[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
-      if (live) tc_epilogue16(p, acc, n_base + c0, er);
+      for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+        float acc[16];
+        float4 mul[4], add[4], sl[4];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int n = n_base + c0 + 4 * qd;
+          mul[qd] = drow ? ldg4(drow + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.ch_scale) {
+            const float4 sc = ldg4(p.ch_scale + n);
+            mul[qd].x *= sc.x; mul[qd].y *= sc.y; mul[qd].z *= sc.z; mul[qd].w *= sc.w;
+          }
+          add[qd] = p.ch_shift ? ldg4(p.ch_shift + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          sl[qd] = make_float4(tc_epi_slope(p, n), tc_epi_slope(p, n + 1), tc_epi_slope(p, n + 2), tc_epi_slope(p, n + 3));
+        }
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+        if (live) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            float4 a;
+            a.x = fmaf(acc[4 * qd], mul[qd].x, add[qd].x + nz); a.y = fmaf(acc[4 * qd + 1], mul[qd].y, add[qd].y + nz);
+            a.z = fmaf(acc[4 * qd + 2], mul[qd].z, add[qd].z + nz); a.w = fmaf(acc[4 * qd + 3], mul[qd].w, add[qd].w + nz);
+            a.x = (a.x < 0.f ? a.x * sl[qd].x : a.x) * gain; a.y = (a.y < 0.f ? a.y * sl[qd].y : a.y) * gain;
+            a.z = (a.z < 0.f ? a.z * sl[qd].z : a.z) * gain; a.w = (a.w < 0.f ? a.w * sl[qd].w : a.w) * gain;
+            reinterpret_cast<float4*>(optr + c0)[qd] = a;
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+        float acc[16];
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+        if (live) tc_epilogue16(p, acc, n_base + c0, er);
+      }
     }
     tc_fence_before();
   } else if (warp == TC_PRODUCER_WARPS) {
