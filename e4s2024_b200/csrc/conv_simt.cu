@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_batched_kernel(const __gri
 
 int validate_conv(const E4SConv* p) {
   E4S_REQUIRE(p != nullptr, "conv: null params");
-  E4S_REQUIRE(p->x && p->w && p->out, "conv: null x/w/out");
+  E4S_REQUIRE(p->x && p->w && (p->out || p->rgb), "conv: null x/w/out");
+  if (p->rgb)
+    E4S_REQUIRE(p->rgb_w && p->rgb_smod && (!p->rgb_skip || p->rgb_fir) && p->cout % 4 == 0, "conv: fused ToRGB needs rgb_w, rgb_smod (and rgb_fir with a skip)");
   E4S_REQUIRE(p->batch > 0 && p->hin > 0 && p->win > 0 && p->hout > 0 && p->wout > 0, "conv: bad shape");
   E4S_REQUIRE(p->cin > 0 && p->cin % 8 == 0, "conv: cin=%d must be a multiple of 8", p->cin);
   E4S_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % 4 == 0, "conv: bad cout/cout_pad %d/%d", p->cout, p->cout_pad);
@@ -296,6 +298,7 @@ extern "C" int e4s_conv_f32(const E4SConv* p, void* stream) {
   using namespace e4s;
   int rc = validate_conv(p);
   if (rc) return rc;
+  E4S_REQUIRE(!p->rgb, "conv_f32: the fused ToRGB tail is implemented by the tensor-core halo kernel only");
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   const int64_t m_total = up ? (int64_t)p->batch * p->hin * p->win : (int64_t)p->batch * p->hout * p->wout;
   const int64_t mt = ceil_div64(m_total, BM);

@@ -452,6 +452,10 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
   E4S_REQUIRE(tc_shape_ok(K, p->cout), "conv_tc: needs cin %% 8 == 0 and cout in {32,64,128,256*n} (cin=%d cout=%d)", p->cin, p->cout);
   E4S_REQUIRE(!p->in_square, "conv_tc: in_square is only implemented by the fp32 engine");
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc: out must be 16-byte aligned with pitch %% 4 == 0");
+  if (p->rgb)
+    E4S_REQUIRE(tc_halo_eligible(p) && p->mode != E4S_CONV_UP2_POLYPHASE && p->cout <= 256 && tc_epi_is_fast(*p) && p->regions == 1 &&
+                    (reinterpret_cast<uintptr_t>(p->rgb_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->rgb_smod) & 15) == 0,
+                "conv_tc: the fused ToRGB tail needs an un-masked same-resolution 3x3 layer of the halo kernel (cout <= 256, piecewise-linear activation)");
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
   if (p->smod) E4S_REQUIRE((reinterpret_cast<uintptr_t>(p->smod) & 15) == 0, "conv_tc: smod must be 16-byte aligned");
   if (p->res) E4S_REQUIRE(p->res_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->res) & 15) == 0, "conv_tc: res must be 16-byte aligned with pitch %% 4 == 0");
@@ -463,7 +467,7 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
     const char* e = getenv("E4S_TC_HALO");
     g_tc_halo = (e && e[0] == '0') ? 0 : 1;
   }
-  if (g_tc_halo && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s, nullptr, nullptr, 0);
+  if ((g_tc_halo || p->rgb) && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s, nullptr, nullptr, 0);
   switch (tc_block_n(p->cout)) {
     case 256: return launch_tc<256>(p, w_packed, m_total, s);
     case 128: return launch_tc<128>(p, w_packed, m_total, s);
@@ -484,7 +488,7 @@ extern "C" int e4s_conv_tc_regions(const E4SConv* p, const void* w_packed, const
   E4S_REQUIRE(p->labels && p->smod, "conv_tc_regions: needs labels and a style table");
   const int K = p->kh * p->kw * p->cin;
   E4S_REQUIRE(tc_shape_ok(K, p->cout) && tc_halo_geometry_ok(p), "conv_tc_regions: geometry not supported by the halo kernel");
-  E4S_REQUIRE(!p->in_square && !p->pixw, "conv_tc_regions: in_square / pixw are not supported here");
+  E4S_REQUIRE(!p->in_square && !p->pixw && !p->rgb, "conv_tc_regions: in_square / pixw / fused ToRGB are not supported here");
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc_regions: out must be 16-byte aligned");
   return tc_launch_halo(p, w_packed, as_stream(stream), reinterpret_cast<const int4*>(jobs), job_count, job_count_host);
 }

@@ -36,7 +36,8 @@ constexpr int HL_MAX_BST = 6;
 constexpr int HL_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
 // phases of an up-convolution merged into the N dimension of one MMA (all four phases read the SAME halo window)
 __host__ __device__ constexpr int hl_phase_merge(int bn, bool up) { return (up && 4 * bn <= 256) ? 4 : 1; }
-__host__ __device__ constexpr int hl_fixed_bytes(int bn) { return HL_HALO_STAGES * 2 * HL_PLANE + 2 * 3 * bn * 4 + 512 + 1024; }
+// fixed part: halo stages + 2 slots of 6 per-channel epilogue vectors (mul | add | slope | 3 ToRGB rows) + barriers + alignment slack
+__host__ __device__ constexpr int hl_fixed_bytes(int bn) { return HL_HALO_STAGES * 2 * HL_PLANE + 2 * 6 * bn * 4 + 512 + 1024; }
 __host__ __device__ constexpr int hl_b_stages(int bn, int pm) {
   int n = (HL_SMEM_MAX - hl_fixed_bytes(bn)) / (2 * pm * bn * 128);
   return n > HL_MAX_BST ? HL_MAX_BST : n;
@@ -112,8 +113,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   // [halo stage 0: hi | lo][halo stage 1: hi | lo][B ring: BST x (hi | lo)][barriers]
   constexpr int HALO_BYTES = 2 * HL_PLANE;
   constexpr int B_OFF = HL_HALO_STAGES * HALO_BYTES;
-  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * STAGE_B);            // [2 slots][mul | add | slope][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * STAGE_B + 2 * 3 * BN * 4);
+  float* s_epi = reinterpret_cast<float*>(smem + B_OFF + BST * STAGE_B);            // [2 slots][mul | add | slope | rgb0 | rgb1 | rgb2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + BST * STAGE_B + 2 * 6 * BN * 4);
   const uint32_t bar_hfull = smem_u32(bars);                 // 2
   const uint32_t bar_hempty = bar_hfull + 16;                // 2
   const uint32_t bar_bfull = bar_hempty + 16;                // up to HL_MAX_BST
@@ -309,6 +310,21 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     const bool noise1 = p.noise && p.noise_sc == 0;
     const bool fast = tc_epi_is_fast(p) && !(dbg & (1 | 2 | 8 | 16 | 128));    // bit7: force the generic epilogue
     const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
+    // fused ToRGB tail (host guarantees: !UP, one n-tile, no region jobs, fast epilogue)
+    const bool do_rgb = !UP && p.rgb != nullptr;
+    const int sk_h = p.hout >> 1, sk_w = p.wout >> 1;
+    // FIR up-sampling of the skip image (upfirdn2d up=2, pad=(2,1), flipped 4x4 kernel): output (y, x) reads the 2x2 skip
+    // pixels (sy0 + a, sx0 + d) with taps (ky0 + 2a, kx0 + 2d); tiles start at even coordinates, so the taps are per-thread constants
+    const int ky0 = ty & 1, kx0 = tx & 1;
+    float fk[4] = {0.f, 0.f, 0.f, 0.f};
+    if (do_rgb && p.rgb_skip) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int d = 0; d < 2; ++d) fk[2 * a + d] = __ldg(p.rgb_fir + (3 - (ky0 + 2 * a)) * 4 + (3 - (kx0 + 2 * d)));
+    }
+    const float rb0 = (do_rgb && p.rgb_bias) ? __ldg(p.rgb_bias) : 0.f, rb1 = (do_rgb && p.rgb_bias) ? __ldg(p.rgb_bias + 1) : 0.f,
+                rb2 = (do_rgb && p.rgb_bias) ? __ldg(p.rgb_bias + 2) : 0.f;
 
     struct RowOps {
       float nz[P], pw[P];
@@ -350,7 +366,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         // the jobs that read that slot before it passed the previous rebuild's barrier.
         kb = jb.b; knt = jb.nt; kreg = jb.reg;
         slot ^= 1;
-        float* svw = s_epi + slot * 3 * BN;
+        float* svw = s_epi + slot * 6 * BN;
         for (int n = tid - 8 * 32; n < BN; n += 128) {
           const int ng = jb.nt * BN + n;
           float mul = drow ? __ldg(drow + ng) : 1.f;
@@ -358,10 +374,31 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           svw[n] = mul;
           svw[BN + n] = p.ch_shift ? __ldg(p.ch_shift + ng) : 0.f;
           svw[2 * BN + n] = tc_epi_slope(p, ng);
+          if (do_rgb) {
+            const float sm = __ldg(p.rgb_smod + (int64_t)jb.b * p.cout + ng);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) svw[(3 + c) * BN + n] = ng < p.cout ? __ldg(p.rgb_w + c * p.cout + ng) * sm : 0.f;
+          }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
       }
-      const float* sv = s_epi + slot * 3 * BN;
+      const float* sv = s_epi + slot * 6 * BN;
+      // skip taps of this pixel: issued before the accumulator wait, consumed (first arithmetic) after the channel loop
+      float skv[12];
+      if (do_rgb && p.rgb_skip) {
+        const int sy0 = (oy0 - 2 + ky0) >> 1, sx0 = (ox0 - 2 + kx0) >> 1;     // arithmetic shift: -1 at the top / left border
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* sp = p.rgb_skip + ((int64_t)jb.b * 3 + c) * sk_h * sk_w;
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              const int sy = sy0 + a, sx = sx0 + d;
+              skv[c * 4 + 2 * a + d] = (sy >= 0 && sy < sk_h && sx >= 0 && sx < sk_w) ? __ldg(sp + (int64_t)sy * sk_w + sx) : 0.f;
+            }
+        }
+      }
       HL_LAP(1, 3);
       mbar_wait(bar_afull + 8 * set, use & 1);
       tc_fence_after();
@@ -372,8 +409,9 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
         const int64_t pix = UP ? pix0 + (ph >> 1) * p.wout + (ph & 1) : pix0;
         const bool live = !need_lab || cur.lab[ph] == (uint32_t)jb.reg;
         if (fast) {
-          float* optr = p.out + pix * p.out_pitch + jb.nt * BN;
+          float* optr = p.out ? p.out + pix * p.out_pitch + jb.nt * BN : nullptr;
           const float nz = nw * cur.nz[ph];
+          float rgb3[3] = {0.f, 0.f, 0.f};
           if (NC) {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -384,7 +422,10 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               tmem_wait_ld16x2(ra, rb);
 #pragma unroll
               for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
-              if (live) tc_epilogue_fast<16>(optr + c0, acc, sv, c0, BN, nz, gain);
+              if (live) {
+                if (do_rgb) tc_epilogue_fast<16, true>(optr ? optr + c0 : nullptr, acc, sv, c0, BN, nz, gain, sv + 3 * BN, rgb3);
+                else tc_epilogue_fast<16>(optr + c0, acc, sv, c0, BN, nz, gain);
+              }
             }
           } else {
 #pragma unroll 1
@@ -395,7 +436,21 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               tmem_wait_ld32(ra);
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(ra[j]);
-              if (live) tc_epilogue_fast<32>(optr + c0, acc, sv, c0, BN, nz, gain);
+              if (live) {
+                if (do_rgb) tc_epilogue_fast<32, true>(optr ? optr + c0 : nullptr, acc, sv, c0, BN, nz, gain, sv + 3 * BN, rgb3);
+                else tc_epilogue_fast<32>(optr + c0, acc, sv, c0, BN, nz, gain);
+              }
+            }
+          }
+          if (do_rgb) {
+            const int64_t hw = (int64_t)p.hout * p.wout;
+            float* ro = p.rgb + (int64_t)jb.b * 3 * hw + (int64_t)oy0 * p.wout + ox0;
+            const float bias3[3] = {rb0, rb1, rb2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float v = rgb3[c] + bias3[c];
+              if (p.rgb_skip) v += fk[0] * skv[c * 4] + fk[1] * skv[c * 4 + 1] + fk[2] * skv[c * 4 + 2] + fk[3] * skv[c * 4 + 3];
+              ro[c * hw] = v;
             }
           }
           continue;

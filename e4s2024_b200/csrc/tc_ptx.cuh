@@ -311,9 +311,9 @@ __host__ __device__ __forceinline__ bool tc_epi_is_fast(const E4SConv& p) {
 __device__ __forceinline__ float tc_epi_slope(const E4SConv& p, const int n) {
   return p.act == E4S_ACT_PRELU ? __ldg(p.act_prelu + n) : (p.act == E4S_ACT_LRELU ? p.act_slope : (p.act == E4S_ACT_RELU ? 0.f : 1.f));
 }
-template <int NV>   // NV consecutive channels (multiple of 4) of one pixel
+template <int NV, bool RGB = false>   // NV consecutive channels (multiple of 4) of one pixel
 __device__ __forceinline__ void tc_epilogue_fast(float* __restrict__ optr, const float (&acc)[NV], const float* sv, const int nl, const int bn,
-                                                 const float nz, const float gain) {
+                                                 const float nz, const float gain, const float* rgbw = nullptr, float* rgb3 = nullptr) {
   float4* o = reinterpret_cast<float4*>(optr);
 #pragma unroll
   for (int q = 0; q < NV / 4; ++q) {
@@ -325,7 +325,15 @@ __device__ __forceinline__ void tc_epilogue_fast(float* __restrict__ optr, const
     a.z = fmaf(acc[4 * q + 2], mul.z, add.z + nz); a.w = fmaf(acc[4 * q + 3], mul.w, add.w + nz);
     a.x = (a.x < 0.f ? a.x * sl.x : a.x) * gain; a.y = (a.y < 0.f ? a.y * sl.y : a.y) * gain;
     a.z = (a.z < 0.f ? a.z * sl.z : a.z) * gain; a.w = (a.w < 0.f ? a.w * sl.w : a.w) * gain;
-    o[q] = a;
+    if (RGB) {
+      // fused ToRGB: three running dot products with the sample's modulated 1x1 weights (rgbw = [3][bn] in shared memory)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(rgbw + c * bn + nl + 4 * q);
+        rgb3[c] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, rgb3[c]))));
+      }
+    }
+    if (optr) o[q] = a;
   }
 }
 

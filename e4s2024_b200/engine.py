@@ -62,6 +62,12 @@ def halo_geometry_ok(cin: int, cout: int, hin: int, win: int, up2: bool, kh: int
     return (4 if up2 else 1) * min(cout, 256) <= 512 and tc_eligible(cin, cout)
 
 
+def rgb_fusable(cin: int, cout: int, h: int, w: int) -> bool:
+    """Can a same-resolution 3x3 layer carry the fused ToRGB tail (e4s_b200.h, struct E4SConv rgb*)?"""
+    return _ENGINE == "tc" and tc_available() and cout <= 256 and halo_geometry_ok(cin, cout, h, w, False) and \
+        os.environ.get("E4S_FUSE_RGB", "1") != "0"
+
+
 def tc_eligible(cin: int, cout: int) -> bool:
     return cin % 8 == 0 and (cout in (32, 64, 128) or (cout >= 256 and cout % 256 == 0))
 
@@ -157,8 +163,10 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
          smod=None, demod=None, labels=None, regions=1, smod_off=0, demod_off=0, pixw=None, ch_scale=None, ch_shift=None,
          noise=None, noise_w=None, res: Optional[View] = None, res_after_act=False, act=L.ACT_NONE, slope=0.0, gain=1.0,
          prelu=None, out: Optional[View] = None, accumulate=False, engine: Optional[str] = None,
-         region_jobs: Optional["RegionJobs"] = None) -> View:
-    """Launch one fused convolution (see struct E4SConv).  Returns the output view."""
+         region_jobs: Optional["RegionJobs"] = None, rgb: Optional[dict] = None, store_out: bool = True) -> Optional[View]:
+    """Launch one fused convolution (see struct E4SConv).  Returns the output view.
+    `rgb` = {"rgb": [B,3,H,W], "w": [3,cout], "smod": [B,cout], "bias": [3]|None, "skip": [B,3,H/2,W/2]|None, "fir": [4,4]|None}
+    adds the fused ToRGB tail (halo kernel only, see rgb_fusable); with store_out=False the activations are never written."""
     b, hin, win = x.bhw
     assert x.c == pw.cin, (x.c, pw.cin)
     pad = (pw.kh // 2) if pad is None else pad
@@ -168,9 +176,12 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
         hv, wv = hin << in_shift, win << in_shift
         hout = (hv + 2 * pad - pw.kh) // stride + 1
         wout = (wv + 2 * pad - pw.kw) // stride + 1
-    if out is None:
+    if not store_out:
+        assert rgb is not None and out is None
+    elif out is None:
         out = View(new_nhwc(b, hout, wout, pw.cout, x.t.device))
-    assert out.bhw == (b, hout, wout) and out.c == pw.cout, (out.bhw, (b, hout, wout), out.c, pw.cout)
+    if out is not None:
+        assert out.bhw == (b, hout, wout) and out.c == pw.cout, (out.bhw, (b, hout, wout), out.c, pw.cout)
     p = L.E4SConv()
     p.x, p.x_pitch = x.ptr, x.pitch
     p.batch, p.hin, p.win, p.cin = b, hin, win, pw.cin
@@ -211,7 +222,19 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     p.act, p.act_slope, p.act_gain = act, slope, gain
     if prelu is not None:
         p.act_prelu = prelu.data_ptr()
-    p.out, p.out_pitch, p.accumulate = out.ptr, out.pitch, int(accumulate)
+    if out is not None:
+        p.out, p.out_pitch, p.accumulate = out.ptr, out.pitch, int(accumulate)
+    else:
+        p.out_pitch = pw.cout
+    if rgb is not None:
+        assert rgb["rgb"].shape == (b, 3, hout, wout) and rgb["rgb"].is_contiguous() and rgb["w"].shape == (3, pw.cout)
+        assert rgb["smod"].numel() == b * pw.cout and rgb["smod"].is_contiguous() and rgb["w"].is_contiguous()
+        p.rgb, p.rgb_w, p.rgb_smod = rgb["rgb"].data_ptr(), rgb["w"].data_ptr(), rgb["smod"].data_ptr()
+        if rgb.get("bias") is not None:
+            p.rgb_bias = rgb["bias"].data_ptr()
+        if rgb.get("skip") is not None:
+            assert rgb["skip"].shape == (b, 3, hout // 2, wout // 2) and rgb["skip"].is_contiguous()
+            p.rgb_skip, p.rgb_fir = rgb["skip"].data_ptr(), rgb["fir"].data_ptr()
     eng = engine or _ENGINE
     use_tc = eng == "tc" and pw.tc is not None
     use_rj = use_tc and region_jobs is not None and labels is not None
@@ -233,8 +256,8 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     launch()
     ev1.record()
     PROFILE.append({"engine": "tc" if use_tc else "f32", "region_jobs": region_jobs.count if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
-                    "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1),
-                    "bytes": 4.0 * (b * hin * win * pw.cin + m_exec * pw.cout)})
+                    "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1), "rgb": rgb is not None,
+                    "bytes": 4.0 * (b * hin * win * pw.cin + (m_exec * pw.cout if out is not None else 0) + (3 * m_exec if rgb is not None else 0))})
     return out
 
 

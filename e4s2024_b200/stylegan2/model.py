@@ -270,14 +270,14 @@ class StyledConv(nn.Module):
         self.activate = FusedLeakyReLU(out_channel)
         self.mask_op = mask_op
 
-    def run(self, x: View, st: StyleRows, ctx, noise, tables=None) -> View:
+    def run(self, x: View, st: StyleRows, ctx, noise, tables=None, **extra) -> View:
         b, h, w = x.bhw
         if self.conv.upsample:
             h, w = 2 * h, 2 * w
         nz = _noise_for(noise, b, h, w, x.t.device)
         return self.conv.run(x, st, ctx if self.mask_op else None, tables=tables, noise=nz, noise_w=self.noise.weight.detach(),
                              ch_shift=self.activate.bias.detach(), act=L.ACT_LRELU,
-                             slope=self.activate.negative_slope, gain=self.activate.scale)
+                             slope=self.activate.negative_slope, gain=self.activate.scale, **extra)
 
     def forward(self, input, style, mask, noise=None):
         x = View(L.nchw_to_nhwc(input.contiguous().float()))
@@ -303,6 +303,18 @@ class ToRGB(nn.Module):
             w = (self.conv.weight.detach()[0, :, :, 0, 0] * self.conv.scale).contiguous().float()    # [3,Ci]
             self._wrgb = (key, w)
         return self._wrgb[1]
+
+    def fused_args(self, b: int, h: int, w: int, s: torch.Tensor, skip: Optional[torch.Tensor], device) -> dict:
+        """Arguments of the ToRGB tail fused into the preceding StyledConv's epilogue (engine.conv `rgb=`): this layer's
+        1x1 modulated conv + bias + FIR-upsampled skip (model.py:439-479) computed from the activations in registers."""
+        fir = None
+        if skip is not None:
+            fir = self.upsample.kernel.detach().float().contiguous()
+            if tuple(fir.shape) != (4, 4) or self.upsample.pad != (2, 1):
+                raise L.E4SError("ToRGB skip path supports the 4-tap FIR (pad=(2,1)) only")
+            skip = skip.contiguous().float()
+        return {"rgb": torch.empty(b, 3, h, w, device=device, dtype=torch.float32), "w": self._weights(), "smod": s,
+                "bias": self.bias.detach().reshape(3).contiguous(), "skip": skip, "fir": fir}
 
     def run(self, x: View, st: StyleRows, ctx, skip: Optional[torch.Tensor], tables=None) -> torch.Tensor:
         """x NHWC view, skip NCHW [B,3,H/2,W/2] or None -> rgb NCHW [B,3,H,W]."""
@@ -467,8 +479,19 @@ class Generator(nn.Module):
                 if use_structure_code:
                     out = View(L.nchw_to_nhwc(structure_feats.contiguous().float()))
                 intermediate_feats = L.nhwc_to_nchw(out.t)
-            out = sconv(conv2, out, noise2)
-            skip = rgb(to_rgb, out, skip)
+            st2, st3 = sty[id(conv2.conv)], sty[id(to_rgb.conv)]
+            _, hh, ww = out.bhw
+            if st2.regions == 1 and st3.regions == 1 and skip is not None and \
+                    E.rgb_fusable(conv2.conv.in_channel, conv2.conv.out_channel, hh, ww):
+                # un-masked resolutions: ToRGB rides in the conv epilogue (the feature map is not read again; the last
+                # layer's 1024^2 x 32 activations are never written at all)
+                fa = to_rgb.fused_args(b, hh, ww, tabs[id(to_rgb.conv)][0], skip, out.t.device)
+                last = to_rgb is self.to_rgbs[-1]
+                out = conv2.run(out, st2, ctx, noise2, tables=tabs[id(conv2.conv)], rgb=fa, store_out=not last)
+                skip = fa["rgb"]
+            else:
+                out = sconv(conv2, out, noise2)
+                skip = rgb(to_rgb, out, skip)
             i += 2
         image = skip
         if return_latents:

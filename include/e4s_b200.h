@@ -95,6 +95,12 @@ typedef struct E4SConv {
   const float* res; int64_t res_pitch; int32_t res_after_act;
   int32_t act; float act_slope, act_gain; const float* act_prelu;
   float* out; int64_t out_pitch; int32_t accumulate;
+  /* Fused ToRGB tail (reference models/stylegan2/model.py:439-479 applied to this layer's activated output without
+   * re-reading it; e4s_conv_tc only, un-masked same-resolution 3x3 layers with cout <= 256):
+   *   rgb[b,c,y,x] = sum_co act_out[b,y,x,co] * rgb_w[c,co] * rgb_smod[b,co] + rgb_bias[c] + FIR-upsample(rgb_skip)[b,c,y,x]
+   * rgb / rgb_skip are NCHW fp32 ([batch,3,hout,wout] / [batch,3,hout/2,wout/2]); rgb_fir is the 4x4 kernel of
+   * Upsample (upfirdn2d up=2, pad=(2,1)).  With rgb set, out may be NULL: the activations are then never written. */
+  float* rgb; const float* rgb_w; const float* rgb_smod; const float* rgb_bias; const float* rgb_skip; const float* rgb_fir;
 } E4SConv;
 
 const char* e4s_last_error(void);
