@@ -396,6 +396,9 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int c
 int validate_conv(const E4SConv* p);
 
 static int g_tc_halo = -1;         // -1: read E4S_TC_HALO (default on)
+static int g_tc_wide = -1;         // -1: read E4S_TC_WIDE (default on)
+bool tc_wide_eligible(const E4SConv* p);
+int tc_launch_wide(const E4SConv* p, const void* wpk, cudaStream_t s);
 bool tc_halo_eligible(const E4SConv* p);
 int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs, const int* rjob_count, int rjob_host_count);
 bool tc_halo_geometry_ok(const E4SConv* p);
@@ -468,6 +471,11 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
     g_tc_halo = (e && e[0] == '0') ? 0 : 1;
   }
   if ((g_tc_halo || p->rgb) && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s, nullptr, nullptr, 0);
+  if (g_tc_wide < 0) {
+    const char* e = getenv("E4S_TC_WIDE");
+    g_tc_wide = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_tc_wide && tc_wide_eligible(p)) return tc_launch_wide(p, w_packed, s);
   switch (tc_block_n(p->cout)) {
     case 256: return launch_tc<256>(p, w_packed, m_total, s);
     case 128: return launch_tc<128>(p, w_packed, m_total, s);

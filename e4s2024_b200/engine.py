@@ -68,6 +68,16 @@ def rgb_fusable(cin: int, cout: int, h: int, w: int) -> bool:
         os.environ.get("E4S_FUSE_RGB", "1") != "0"
 
 
+def wide_eligible(cin: int, cout: int, hin: int, win: int, up2: bool) -> bool:
+    """Mirror of tc_wide_eligible (conv_tc_wide.cu) for the StyledConv epilogue: geometry of the 512-column gather kernel."""
+    if _ENGINE != "tc" or os.environ.get("E4S_TC_WIDE", "1") == "0" or cin % 64 or hin % 16 or win % 8:
+        return False
+    return cout % 128 == 0 if up2 else cout % 512 == 0
+
+
+WIDE_OVER_REGION_JOBS = float(os.environ.get("E4S_WIDE_RATIO", "1.25"))
+
+
 def tc_eligible(cin: int, cout: int) -> bool:
     return cin % 8 == 0 and (cout in (32, 64, 128) or (cout >= 256 and cout % 256 == 0))
 
@@ -327,10 +337,13 @@ class RegionCtx:
             gh, gw = (h // 2, w // 2) if up else (h, w)
             self.region_jobs[key] = RegionJobs(jl, meta[1 + i:2 + i], int(host[1 + i]), b * (gh // 16) * (gw // 8))
 
-    def jobs_for(self, hout: int, wout: int, up2: bool) -> Optional["RegionJobs"]:
-        """The job list if this resolution has few enough regions per tile for the halo kernel to win."""
+    def jobs_for(self, hout: int, wout: int, up2: bool, wide_ok: bool = False) -> Optional["RegionJobs"]:
+        """The job list if this resolution has few enough regions per tile for the halo kernel to win
+        (`wide_ok`: the layer can run on the 512-column gather kernel, which costs one pass whatever the mask)."""
         rj = self.region_jobs.get((hout, wout, bool(up2)))
         if rj is None or not self.onehot or rj.count <= 0 or rj.count > REGION_JOB_RATIO * rj.tiles:
+            return None
+        if wide_ok and rj.count > WIDE_OVER_REGION_JOBS * rj.tiles:
             return None
         return rj
 

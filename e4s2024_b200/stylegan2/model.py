@@ -202,7 +202,7 @@ class ModulatedConv2d(nn.Module):
             if regional:
                 _, h, w = x.bhw
                 ho, wo = (2 * h, 2 * w) if self.upsample else (h, w)
-                rj = ctx.jobs_for(ho, wo, self.upsample)
+                rj = ctx.jobs_for(ho, wo, self.upsample, E.wide_eligible(self.in_channel, self.out_channel, h, w, self.upsample))
             return E.conv(x, conv, up2=self.upsample, smod=s, demod=d, regions=st.regions,
                           labels=ctx.labels if regional else None, region_jobs=rj, **epilogue)
         # generic float masks: sum_k mask_k * conv(x; style_k), then the epilogue (model.py:395-398)

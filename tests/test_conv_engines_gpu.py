@@ -35,6 +35,13 @@ CASES = [
     ("halo_up2_c64_n32", 2, 16, 16, 64, 32, 3, 1, True, 1),
     ("halo_up2_c128_n64", 2, 16, 8, 128, 64, 3, 1, True, 1),
     ("halo_up2_c32_n32", 1, 32, 16, 32, 32, 3, 1, True, 1),
+    # geometries taken by the 512-column gather kernel (conv_tc_wide.cu): merged tiles (one region per sample or a coarse
+    # mask), mixed tiles (per-pixel random labels -> the four phases of a pixel differ -> per-phase passes)
+    ("wide_up2_c128_n128", 2, 16, 16, 128, 128, 3, 1, True, 1),
+    ("wide_up2_c64_n256_mixed", 1, 32, 16, 64, 256, 3, 1, True, 6),
+    ("wide_up2_c64_n128_coarse", 2, 16, 16, 64, 128, 3, 1, True, -4),
+    ("wide_c64_n512_regions", 1, 32, 16, 64, 512, 3, 1, False, 7),
+    ("wide_c128_n1024", 1, 16, 8, 128, 1024, 3, 1, False, 1),
 ]
 
 
@@ -45,12 +52,16 @@ def test_tc_matches_f32_and_torch(case):
     if not E.tc_available():
         pytest.skip("library built without the tcgen05 engine")
     name, B, H, W, Cin, Cout, k, stride, up2, R = case
+    coarse = R < 0            # labels constant over 8x8 blocks of the 32x32 label map: phase-uniform rows (merged tiles)
+    R = abs(R)
     x = _mk((B, H, W, Cin), name + ".x")
     w = _mk((Cout, Cin, k, k), name + ".w", (1.0 / (Cin * k * k)) ** 0.5)
     Ho, Wo = (2 * H, 2 * W) if up2 else ((H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1)
     smod = (1.0 + 0.3 * _mk((B, R, Cin), name + ".s")).contiguous()
     demod = (1.0 + 0.2 * _mk((B, R, Cout), name + ".d")).contiguous()
     labels = torch.randint(0, R, (B, 32, 32), device="cuda", dtype=torch.uint8) if R > 1 else None
+    if coarse:
+        labels = torch.randint(0, R, (B, 4, 4), device="cuda", dtype=torch.uint8).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
     noise = _mk((1, 1, Ho, Wo), name + ".n")
     nw = torch.tensor([0.1], device="cuda")
     bias = _mk((Cout,), name + ".b", 0.1)
