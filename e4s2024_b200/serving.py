@@ -1,0 +1,78 @@
+"""Host <-> device streaming around the hot path: overlap the PCIe copies of batch i+1 / i-1 with the kernels of batch i.
+
+The reference pipelines (face_swap_video_pipeline.py:430-443) run batch 1 and copy synchronously; at 16 faces per
+batch the one-hot mask (201 MB) and the images (201 MB) cost as much PCIe time as the whole synthesis costs kernel time,
+so a serving loop has to double-buffer them.  This module is plumbing only (pinned buffers, three CUDA streams,
+events); every computation stays inside the callable it is given (the drop-in modules -> libe4s_b200.so).
+
+    pipe = HostPipeline(lambda lat, msk: G([lat], None, msk, input_is_latent=True, randomize_noise=False)[0], device)
+    for lat_h, msk_h, out_h in batches:        # pinned host tensors
+        pipe.submit((lat_h, msk_h), out_h)
+    pipe.drain()
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+
+class HostPipeline:
+    """Double-buffered H2D -> fn -> D2H.  `submit` returns immediately; results are complete after `drain()` (or after
+    `depth` further submits).  Inputs must be pinned host tensors for the copies to be asynchronous."""
+
+    def __init__(self, fn: Callable[..., torch.Tensor], device: torch.device, depth: int = 2):
+        if device.type != "cuda":
+            raise RuntimeError("HostPipeline needs a CUDA device (there is no CPU path)")
+        self.fn, self.dev, self.depth = fn, device, depth
+        self.s_in = torch.cuda.Stream(device)
+        self.s_out = torch.cuda.Stream(device)
+        self.slots = [None] * depth            # device input buffers per slot
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of the slot are resident
+        self.ev_used = [torch.cuda.Event() for _ in range(depth)]     # fn has consumed the slot's inputs
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # result of the slot is on the host
+        self.pending: list = [None] * depth    # (inputs_host, out_host) staged for the slot, not yet computed
+        self.n_staged = 0
+        self.n_run = 0
+
+    def _stage(self, inputs: Sequence[torch.Tensor]):
+        """H2D of one batch into the next slot on the copy-in stream."""
+        slot = self.n_staged % self.depth
+        if self.slots[slot] is None:
+            self.slots[slot] = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in inputs]
+        with torch.cuda.stream(self.s_in):
+            if self.n_staged >= self.depth:
+                self.s_in.wait_event(self.ev_used[slot])       # the previous user of this slot has read its inputs
+            for d, h in zip(self.slots[slot], inputs):
+                d.copy_(h, non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        self.n_staged += 1
+        return slot
+
+    def submit(self, inputs: Sequence[torch.Tensor], out_host: Optional[torch.Tensor]):
+        """Queue one batch.  The batch submitted one call earlier is computed now (its copy overlapped that call's kernels)."""
+        slot = self._stage(inputs)
+        self.pending[slot] = out_host
+        if self.n_staged - self.n_run >= self.depth:
+            self._run_one()
+
+    def _run_one(self):
+        slot = self.n_run % self.depth
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ev_in[slot])
+        img = self.fn(*self.slots[slot])
+        self.ev_used[slot].record(cur)
+        out_host = self.pending[slot]
+        if out_host is not None:
+            self.s_out.wait_event(self.ev_used[slot])
+            img.record_stream(self.s_out)
+            with torch.cuda.stream(self.s_out):
+                out_host.copy_(img, non_blocking=True)
+                self.ev_out[slot].record(self.s_out)
+        self.n_run += 1
+
+    def drain(self):
+        while self.n_run < self.n_staged:
+            self._run_one()
+        self.s_out.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()

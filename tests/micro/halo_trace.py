@@ -6,10 +6,10 @@ import numpy as np
 import torch
 from e4s2024_b200 import _lib as L, engine as E
 
-B, H, W, Cin, Cout = 16, 1024, 1024, int(sys.argv[1]) if len(sys.argv) > 1 else 32, int(sys.argv[2]) if len(sys.argv) > 2 else 32
+B, Cin, Cout = 16, int(sys.argv[1]) if len(sys.argv) > 1 else 32, int(sys.argv[2]) if len(sys.argv) > 2 else 32
 up2 = len(sys.argv) > 3 and sys.argv[3] == "up"
-if up2:
-    H = W = 512
+RES = int(sys.argv[4]) if len(sys.argv) > 4 else 1024          # output resolution
+H = W = RES // 2 if up2 else RES
 x = torch.randn(B, H, W, Cin, device="cuda")
 w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
 fir = torch.tensor([1., 3., 3., 1.]); fir = (torch.outer(fir, fir) / 16).cuda()
@@ -21,11 +21,6 @@ nw = torch.tensor([0.1], device="cuda"); bias = torch.randn(Cout, device="cuda")
 kw = dict(up2=up2, smod=smod, demod=demod, regions=1, noise=noise, noise_w=nw, ch_shift=bias, act=L.ACT_LRELU, slope=0.2, gain=1.4)
 out = E.conv(E.View(x), pw, engine="tc", **kw)
 torch.cuda.synchronize()
-for flags in (0, 1, 8, 16, 24, 7):
-    L.lib().e4s_debug_halo_flags(flags)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); E.conv(E.View(x), pw, engine="tc", out=out, **kw); e1.record(); torch.cuda.synchronize()
-    print(f"flags {flags}: kernel {e0.elapsed_time(e1):.3f} ms (no trace)")
 cap = 64
 LAPS = {0: ("producer", {0: "loop", 1: "wait hempty", 2: "convert+st.shared", 3: "fence+arrive", 4: "prefetch issue"}),
         1: ("epilogue", {0: "job setup", 3: "sv rebuild", 1: "wait afull", 2: "tmem ld + math + stores + arrive"}),

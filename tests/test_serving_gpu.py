@@ -1,0 +1,33 @@
+"""GPU: the double-buffered host pipeline (e4s2024_b200/serving.py) returns, batch for batch, exactly what a direct
+Generator.forward on device tensors returns -- overlapping the PCIe copies must not change a bit."""
+import pytest
+import torch
+
+from e4s2024_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_host_pipeline_bit_exact():
+    from e4s2024_b200.serving import HostPipeline
+    from e4s2024_b200.stylegan2.model import Generator
+    G = Generator(256, 512, 8, split_layer_idx=5, remaining_layer_idx=13)
+    synth.synth_module_weights(G, seed=6)
+    G = G.cuda().eval()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def fn(lat, msk):
+        return G([lat], None, msk, input_is_latent=True, randomize_noise=False)[0]
+
+    batches = []
+    for i in range(5):
+        lat = synth.randn(f"pipe.latent{i}", (2, 12, 18, 512), 30 + i).pin_memory()
+        msk = synth.onehot(synth.blocky_labels(2, 12, 512, cells=32, seed=30 + i), 12).pin_memory()
+        batches.append((lat, msk, torch.empty(2, 3, 256, 256).pin_memory()))
+    pipe = HostPipeline(fn, dev)
+    for lat, msk, out in batches:
+        pipe.submit((lat, msk), out)
+    pipe.drain()
+    for lat, msk, out in batches:
+        ref = fn(lat.cuda(), msk.cuda()).cpu()
+        assert torch.equal(out, ref)
