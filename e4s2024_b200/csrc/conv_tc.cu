@@ -334,8 +334,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   } else {
     // =========================== B loader (bulk-copy engine) ======================================
     {
-      const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
-      const uint8_t* src = wpk + ((int64_t)phase_id * gridDim.y + n_tile) * num_kc * tile_bytes;
+      const int phases = up ? 4 : 1;
+      const int64_t chunk_bytes = 2 * (int64_t)phases * B_BYTES;             // [hi: phases][lo: phases] per (n_tile, chunk)
+      const uint8_t* src = wpk + (int64_t)n_tile * num_kc * chunk_bytes + (int64_t)phase_id * B_BYTES;
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % STAGES;
         const uint32_t par = (kc / STAGES) & 1;
@@ -343,7 +344,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * TC_A_BYTES;
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_BYTES);
-          bulk_g2s(dst, src + kc * tile_bytes, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous in the packed image
+          if (phases == 1) {
+            bulk_g2s(dst, src + kc * chunk_bytes, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous
+          } else {
+            bulk_g2s(dst, src + kc * chunk_bytes, B_BYTES, bar_full + 8 * s);
+            bulk_g2s(dst + B_BYTES, src + kc * chunk_bytes + (int64_t)phases * B_BYTES, B_BYTES, bar_full + 8 * s);
+          }
         }
         __syncwarp();
       }
@@ -357,10 +363,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   }
 }
 
-// w_f32 [phases][K][cout_pad] -> per (phase, n_tile, k_chunk): B_hi tile | B_lo tile, each BN rows x 128 bytes,
-// row n holds k = chunk*64 .. +63 (bf16) with the 16-byte chunks XOR-swizzled by (n % 8)  == the smem image.
-__global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int cin, int cout, int cout_pad, int bn, uint8_t* __restrict__ out,
-                                       int64_t total) {
+// w_f32 [phases][K][cout_pad] -> per (n_tile, k_chunk): [hi tiles of phase 0..P-1 | lo tiles of phase 0..P-1], each tile BN
+// rows x 128 bytes; row n holds k = chunk*64 .. +63 (bf16) with the 16-byte chunks XOR-swizzled by (n % 8) == the smem
+// image.  Phase-inner, so a kernel that merges the phases of an up-convolution along N (halo: PM = 4, wide: slot pairs)
+// fetches a whole K chunk with ONE bulk copy; a single phase is two copies (hi, lo).
+__global__ void pack_weights_tc_kernel(const float* __restrict__ w, int phases, int K, int cin, int cout, int cout_pad, int bn,
+                                       uint8_t* __restrict__ out, int64_t total) {
   const int num_kc = (K + TC_BK - 1) / TC_BK, nt = cout / bn;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // i enumerates (phase, n_tile, kc, n_local, kpair) with kpair = 32 bf16 pairs per row
@@ -385,11 +393,11 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int K, int c
     const float b = k + 1 < K ? w[((int64_t)ph * K + k + 1) * cout_pad + n] : 0.f;
     const uint32_t h = pack_bf16x2(a, b);
     const uint32_t l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
-    const int64_t tile = (((int64_t)ph * nt + ntile) * num_kc + kc) * (2 * (int64_t)bn * 128);
+    const int64_t tile = (((int64_t)ntile * num_kc + kc) * phases) * (2 * (int64_t)bn * 128);     // chunk base: hi[phases] | lo[phases]
     const int chunk = (kp >> 2) ^ (nl & 7);
     const int64_t off = (int64_t)nl * 128 + chunk * 16 + (kp & 3) * 4;
-    *reinterpret_cast<uint32_t*>(out + tile + off) = h;
-    *reinterpret_cast<uint32_t*>(out + tile + (int64_t)bn * 128 + off) = l;
+    *reinterpret_cast<uint32_t*>(out + tile + (int64_t)ph * bn * 128 + off) = h;
+    *reinterpret_cast<uint32_t*>(out + tile + (int64_t)(phases + ph) * bn * 128 + off) = l;
   }
 }
 
@@ -443,7 +451,7 @@ extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int ci
   const int64_t total = (int64_t)phases * (cout / bn) * ((k + TC_BK - 1) / TC_BK) * bn * 32;
   int64_t g = ceil_div64(total, 256);
   if (g > 148 * 32) g = 148 * 32;
-  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, k, cin, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
+  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, phases, k, cin, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
   return check_launch("pack_weights_tc");
 }
 

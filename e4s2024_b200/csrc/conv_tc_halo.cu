@@ -58,6 +58,7 @@ struct HlJob {
 __device__ unsigned long long* g_hl_trace = nullptr;
 __device__ int g_hl_trace_cap = 0;
 __device__ int g_hl_dbg = 0;      // profiling experiments: bit0 skip epilogue math+stores, bit1 skip tcgen05.ld, bit2 skip MMAs
+#ifdef E4S_HL_ACCT                  // E4S_HL_ACCT=1 python -m e4s2024_b200.build --force  (tests/micro/halo_trace.py)
 #define HL_LAP(role, k)                                   \
   do {                                                    \
     if (acct) {                                           \
@@ -66,6 +67,11 @@ __device__ int g_hl_dbg = 0;      // profiling experiments: bit0 skip epilogue m
       acct_t = n_;                                        \
     }                                                     \
   } while (0)
+#else                               // the predicated-off laps still cost ~20 issue slots per weight chunk in the MMA warp
+#define HL_LAP(role, k) \
+  do {                  \
+  } while (0)
+#endif
 
 // UMMA descriptor words.  The 64-bit shared-memory descriptor is affine in the byte address through its low word only
 // (14-bit start-address field in 16-byte units, smem < 256 KB => no carry), so the issue loop does 32-bit adds on the low
@@ -87,7 +93,7 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint
       : "memory");
 }
 
-template <int BN, bool UP>
+template <int BN, bool UP, bool C32>
 __global__ void __launch_bounds__(HL_THREADS, 1)   // 14 warps are allocated as 16: 128 registers per thread is the ceiling
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
                     const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count) {
@@ -128,11 +134,11 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   const int dbg = g_hl_dbg;                                  // read ONCE (a global load per use otherwise)
   const bool acct = g_hl_trace != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 8 * 32 || tid == HL_MMA_WARP * 32 || tid == (HL_MMA_WARP + 1) * 32);
   long long acct_t = 0;
-  const int cin_eff = p.cin < 64 ? p.cin : 64;               // channels per halo row actually used
-  const int G = p.cin < 64 ? 1 : p.cin / 64;                 // 64-channel groups
-  const int ksteps = cin_eff / 16;
-  const int tpc = 64 / cin_eff;                              // taps per packed 64-wide K chunk (1, or 2 when cin == 32)
-  const int CPG = (9 + tpc - 1) / tpc;                       // packed chunks per (phase, group)
+  constexpr int cin_eff = C32 ? 32 : 64;                     // channels per halo row actually used (cin == 32 or cin % 64 == 0)
+  const int G = C32 ? 1 : p.cin / 64;                        // 64-channel groups
+  constexpr int ksteps = cin_eff / 16;
+  constexpr int tpc = 64 / cin_eff;                          // taps per packed 64-wide K chunk (1, or 2 when cin == 32)
+  constexpr int CPG = (9 + tpc - 1) / tpc;                   // packed chunks per (phase, group)
   const int num_kc = (9 * p.cin + 63) / 64;
   // masked layers: one job per (tile, region present in the tile) from a device-built list (e4s_region_tile_jobs);
   // the halo is modulated with that region's style and the epilogue keeps only the rows that belong to the region
@@ -140,6 +146,15 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   const int my_jobs = total_jobs > (int)blockIdx.x ? (total_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   // every weight chunk of a job fits the ring and all jobs use the same tiles: load once, keep resident
   const bool resident = n_tiles == 1 && G * PL * CPG <= BST;
+  // Cluster launch (n_tiles == 1: every CTA walks the same weight chunk sequence): each CTA fetches 1/csz of every
+  // stage from L2 and multicasts it to all CTAs of the cluster -> L2->SM weight traffic / csz (the 64..128-channel
+  // layers re-stream 150 KB..1.1 MB of weights per 128-pixel job and were bound by exactly that traffic).  A stage is
+  // refilled when EVERY CTA's MMAs have read it: tcgen05.commit multicast arrives on bempty of all CTAs (count = csz).
+  const uint32_t csz = cluster_nctas(), crank = cluster_rank();
+  const bool mcast = csz > 1 && !resident;
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
+  // all CTAs of a cluster must run the same number of weight-ring iterations: pad with weight-only jobs
+  const int ring_jobs = mcast ? (total_jobs + (int)gridDim.x - 1) / (int)gridDim.x : my_jobs;
   const bool pow2 = ((tiles_x & (tiles_x - 1)) | (tiles_y & (tiles_y - 1))) == 0;
   const int sx_sh = 31 - __clz(tiles_x), sy_sh = 31 - __clz(tiles_y);
 
@@ -185,7 +200,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     }
     for (int s = 0; s < HL_MAX_BST; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
-      mbar_init(bar_bempty + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, mcast ? csz : 1);
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -193,6 +208,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   if (warp == HL_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();                          // barrier inits visible cluster-wide before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (acct) acct_t = clock64();
@@ -489,111 +505,142 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       cur = nxt;
     }
   } else if (warp == HL_MMA_WARP) {
-    // =========================== MMA issuer (whole warp walks the loops, one elected lane issues) ==
-    constexpr uint32_t A_HI = umma_desc_hi(HL_HP * 128), B_HI = umma_desc_hi(1024);
-    const uint32_t kb16 = (uint32_t)(cin_eff * 2) >> 4;     // 16-byte units per tap inside a packed 64-wide K chunk
-    int hg = 0, bs = 0, bph = 0;                             // running halo-fill counter, weight stage and its phase parity
-    for (int it = 0; it < my_jobs; ++it) {
-      if (resident) bs = 0;                                  // resident weights: chunk i of every job lives in stage i
-      const int set = NSETS == 2 ? (it & 1) : 0;
-      const int use = NSETS == 2 ? (it >> 1) : it;
-      HL_LAP(2, 0);
-      mbar_wait(bar_aempty + 8 * set, (use & 1) ^ 1);
-      tc_fence_after();
-      HL_LAP(2, 1);
-      for (int g = 0; g < G; ++g, ++hg) {
-        const int hs = hg & 1;
-        mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
-        HL_LAP(2, 2);
+    // =========================== MMA issuer =========================================================
+    // ONE elected thread runs the whole role: the instruction stream of this warp is the critical path of the kernel
+    // (profiles/r1_halo_accounting_*.txt: ~450 cycles of loop overhead per weight chunk before this rewrite), so the tap /
+    // K-step loops are unrolled with compile-time descriptor offsets and there is no per-chunk elect / syncwarp.
+    if (elect_one()) {
+      constexpr uint32_t A_HI = umma_desc_hi(HL_HP * 128), B_HI = umma_desc_hi(1024);
+      constexpr uint32_t kb16 = (uint32_t)(cin_eff * 2) >> 4;   // 16-byte units per tap inside a packed 64-wide K chunk
+      const uint32_t b_ring = umma_desc_lo(smem_base + B_OFF);
+      int hg = 0, bs = 0, bph = 0;                             // running halo-fill counter, weight stage and its phase parity
+      for (int it = 0; it < my_jobs; ++it) {
+        if (resident) bs = 0;                                  // resident weights: chunk i of every job lives in stage i
+        const int set = NSETS == 2 ? (it & 1) : 0;
+        const int use = NSETS == 2 ? (it >> 1) : it;
+        HL_LAP(2, 0);
+        mbar_wait(bar_aempty + 8 * set, (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_h = umma_desc_lo(smem_base + hs * HALO_BYTES), a_l = umma_desc_lo(smem_base + hs * HALO_BYTES + HL_PLANE);
+        HL_LAP(2, 1);
+        for (int g = 0; g < G; ++g, ++hg) {
+          const int hs = hg & 1;
+          mbar_wait(bar_hfull + 8 * hs, (hg >> 1) & 1);
+          HL_LAP(2, 2);
+          tc_fence_after();
+          const uint32_t a_h = umma_desc_lo(smem_base + hs * HALO_BYTES), a_l = a_h + (HL_PLANE >> 4);
 #pragma unroll
-        for (int pl = 0; pl < PL; ++pl) {
-          const uint32_t tacc = tmem_base + (uint32_t)(set * ACC_COLS + pl * PM * BN);
-          int tap = 0;
-          for (int c = 0; c < CPG; ++c) {
-            HL_LAP(2, 5);
-            if (!resident || it == 0) {
-              mbar_wait(bar_bfull + 8 * bs, bph);
-              tc_fence_after();
-            }
-            HL_LAP(2, 4);
-            const uint32_t b_h = umma_desc_lo(smem_base + B_OFF + bs * STAGE_B), b_l = b_h + ((PM * B_BYTES) >> 4);
-            if (elect_one()) {
+          for (int pl = 0; pl < PL; ++pl) {
+            const uint32_t tacc = tmem_base + (uint32_t)(set * ACC_COLS + pl * PM * BN);
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) {
+              HL_LAP(2, 5);
+              if (!resident || it == 0) {
+                mbar_wait(bar_bfull + 8 * bs, bph);
+                tc_fence_after();
+              }
+              HL_LAP(2, 4);
+              const uint32_t b_h = b_ring + (uint32_t)bs * (STAGE_B >> 4), b_l = b_h + ((PM * B_BYTES) >> 4);
               if (!(dbg & 4)) {
-                uint32_t boff = 0;
-                for (int tt = 0; tt < tpc && tap + tt < 9; ++tt, boff += kb16) {
-                  const int t9 = tap + tt;
-                  const uint32_t aoff = (uint32_t)((t9 / 3) * HL_HP + (t9 % 3)) * 8u;
-                  for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t ao = aoff + 2 * k, bo = boff + 2 * k;
-                    const uint32_t first = (uint32_t)((g | t9 | k) != 0);
-                    if (NC) {
-                      umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC2, first);   // A_hi x [B_hi ; B_lo] -> both accumulator halves
-                      umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, 1);        // A_lo x B_hi        -> first half
-                    } else {
-                      umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, first);
-                      umma_bf16_w(tacc, a_h + ao, A_HI, b_l + bo, B_HI, IDESC, 1);
-                      umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC, 1);
+#pragma unroll
+                for (int tt = 0; tt < tpc; ++tt) {
+                  const int t9 = c * tpc + tt;
+                  if (t9 < 9) {
+                    const uint32_t aoff = (uint32_t)((t9 / 3) * HL_HP + (t9 % 3)) * 8u;
+                    const uint32_t boff = (uint32_t)tt * kb16;
+#pragma unroll
+                    for (int k = 0; k < ksteps; ++k) {
+                      const uint32_t ao = aoff + 2 * k, bo = boff + 2 * k;
+                      const uint32_t first = (t9 | k) != 0 ? 1u : (uint32_t)(g != 0);
+                      if (NC) {
+                        umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC2, first);   // A_hi x [B_hi ; B_lo] -> both accumulator halves
+                        umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, 1);        // A_lo x B_hi        -> first half
+                      } else {
+                        umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, first);
+                        umma_bf16_w(tacc, a_h + ao, A_HI, b_l + bo, B_HI, IDESC, 1);
+                        umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC, 1);
+                      }
                     }
                   }
                 }
               }
-              if (!resident) umma_commit(bar_bempty + 8 * bs);
-            }
-            __syncwarp();
-            tap += tpc;
-            if (++bs == BST) {
-              bs = 0;
-              bph ^= 1;
+              if (!resident) {
+                if (mcast) umma_commit_mc(bar_bempty + 8 * bs, cmask);
+                else umma_commit(bar_bempty + 8 * bs);
+              }
+              if (++bs == BST) {
+                bs = 0;
+                bph ^= 1;
+              }
             }
           }
+          umma_commit(bar_hempty + 8 * hs);                    // every tap of every phase has read this halo
         }
-        if (elect_one()) umma_commit(bar_hempty + 8 * hs);    // every tap of every phase has read this halo
-        __syncwarp();
+        umma_commit(bar_afull + 8 * set);
+        HL_LAP(2, 3);
       }
-      if (elect_one()) umma_commit(bar_afull + 8 * set);
-      __syncwarp();
-      HL_LAP(2, 3);
+      // weight-only padding jobs: keep this CTA's share of the cluster's weight ring turning (release every stage unread)
+      for (int it = my_jobs; it < ring_jobs; ++it)
+        for (int c = 0; c < G * PL * CPG; ++c) {
+          mbar_wait(bar_bfull + 8 * bs, bph);
+          tc_fence_after();
+          umma_commit_mc(bar_bempty + 8 * bs, cmask);
+          if (++bs == BST) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
     }
     __syncwarp();
   } else {
-    // =========================== weight loader ====================================================
-    const int64_t tile_bytes = 2 * (int64_t)B_BYTES;
-    int bs = 0, bph = 0;
-    for (int it = 0; it < (resident ? (my_jobs > 0 ? 1 : 0) : my_jobs); ++it) {
-      const HlJob jb = decode(it);
-      for (int g = 0; g < G; ++g)
-        for (int pl = 0; pl < PL; ++pl)
-          for (int c = 0; c < CPG; ++c) {
-            const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
-            HL_LAP(3, 1);
-            mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
-            HL_LAP(3, 0);
-            if (dbg & 64) {
-              if (elect_one()) mbar_arrive(bar_bfull + 8 * bs);
-            } else if (elect_one()) {
-              const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
-              mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
-#pragma unroll
-              for (int q = 0; q < PM; ++q) {               // hi tiles of the merged phases back to back, then the lo tiles
-                const uint8_t* src = wpk + (((int64_t)(pl * PM + q) * n_tiles + jb.nt) * num_kc + kc) * tile_bytes;
-                bulk_g2s(dst + q * B_BYTES, src, B_BYTES, bar_bfull + 8 * bs);
-                bulk_g2s(dst + (PM + q) * B_BYTES, src + B_BYTES, B_BYTES, bar_bfull + 8 * bs);
+    // =========================== weight loader (one elected thread) ================================
+    if (elect_one()) {
+      int bs = 0, bph = 0;
+      for (int it = 0; it < (resident ? (my_jobs > 0 ? 1 : 0) : ring_jobs); ++it) {
+        HlJob jb = decode(it < my_jobs ? it : 0);
+        if (mcast) jb.nt = 0;
+        for (int g = 0; g < G; ++g)
+          for (int pl = 0; pl < PL; ++pl)
+            for (int c = 0; c < CPG; ++c) {
+              const int kc = tpc == 1 ? g * 9 + c : c;       // packed chunk order: channel group outer, tap inner (pack_weights_tc)
+              HL_LAP(3, 1);
+              mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+              HL_LAP(3, 0);
+              if (dbg & 64) {
+                mbar_arrive(bar_bfull + 8 * bs);
+              } else {
+                const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
+                // packed chunk (e4s_pack_weights_tc): [hi tiles of the P phases | lo tiles of the P phases]
+                const uint8_t* src = wpk + ((int64_t)jb.nt * num_kc + kc) * (2 * (int64_t)P * B_BYTES);
+                if (mcast) {                                 // this CTA's slice of the stage, to every CTA of the cluster
+                  const uint32_t slice = (uint32_t)STAGE_B / csz;
+                  if (PM == P) {
+                    bulk_g2s_mc(dst + crank * slice, src + crank * slice, slice, bar_bfull + 8 * bs, cmask);
+                  } else {                                   // stage = [hi tile | lo tile] of phase pl: a slice never straddles the two
+                    const uint32_t off = crank * slice;
+                    const uint8_t* sp = off < (uint32_t)B_BYTES ? src + (int64_t)pl * B_BYTES + off : src + (int64_t)(P + pl) * B_BYTES + (off - B_BYTES);
+                    bulk_g2s_mc(dst + off, sp, slice, bar_bfull + 8 * bs, cmask);
+                  }
+                } else if (PM == P) {                        // every phase merged (or a plain conv): the stage IS the chunk
+                  bulk_g2s(dst, src, STAGE_B, bar_bfull + 8 * bs);
+                } else {                                     // one phase per MMA group
+                  bulk_g2s(dst, src + (int64_t)pl * B_BYTES, B_BYTES, bar_bfull + 8 * bs);
+                  bulk_g2s(dst + B_BYTES, src + (int64_t)(P + pl) * B_BYTES, B_BYTES, bar_bfull + 8 * bs);
+                }
+              }
+              if (++bs == BST) {
+                bs = 0;
+                bph ^= 1;
               }
             }
-            __syncwarp();
-            if (++bs == BST) {
-              bs = 0;
-              bph ^= 1;
-            }
-          }
+      }
     }
     __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();                          // no CTA may exit while a peer can still multicast into it
   if (warp == HL_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -641,13 +688,14 @@ __global__ void __launch_bounds__(128) region_tile_jobs_kernel(const uint8_t* __
 }
 
 static int g_halo_sm_count = 0;
+static int g_halo_cluster = -1;
 
 // geometry the halo kernel takes (everything else stays on the gather kernel)
 bool tc_halo_geometry_ok(const E4SConv* p) {
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   if (!up && !(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && p->in_shift == 0)) return false;
   if (p->hin % HL_TH || p->win % HL_TW) return false;
-  if (!(p->cin == 32 || p->cin % 64 == 0)) return false;
+  if (!((p->cin == 32 && p->cout == 32) || p->cin % 64 == 0)) return false;   // cin == 32 is instantiated for the 32 -> 32 layers only
   const int bn = tc_block_n(p->cout);
   if ((up ? 4 : 1) * bn > 512) return false;
   return true;
@@ -658,14 +706,14 @@ bool tc_halo_eligible(const E4SConv* p) {
   return tc_halo_geometry_ok(p);
 }
 
-template <int BN, bool UP>
+template <int BN, bool UP, bool C32 = false>
 static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs = nullptr, const int* rjob_count = nullptr,
                        int rjob_host_count = 0) {
   static bool attr_set = false;
   constexpr int pm = hl_phase_merge(BN, UP);
   constexpr int smem_bytes = hl_smem_bytes(BN, pm);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, UP, C32>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX);
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -679,8 +727,38 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
   const int64_t total = rjobs ? (int64_t)rjob_host_count * n_tiles : (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
   E4S_REQUIRE(total > 0 && total < 0x7fffffff, "conv_tc(halo): bad job count");
   const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
-  conv_tc_halo_kernel<BN, UP><<<grid, HL_THREADS, smem_bytes, s>>>(*p, static_cast<const uint8_t*>(wpk), tiles_x, tiles_y, n_tiles,
-                                                                     (int)total, rjobs, rjob_count);
+  // cluster size for the weight multicast (E4S_HALO_CLUSTER = 1 | 2 | 4, default 2): full persistent grids with one n-tile only
+  if (g_halo_cluster < 0) {
+    const char* e = getenv("E4S_HALO_CLUSTER");
+    g_halo_cluster = e ? atoi(e) : 2;
+    if (g_halo_cluster != 1 && g_halo_cluster != 2 && g_halo_cluster != 4) g_halo_cluster = 2;
+  }
+  unsigned csz = (n_tiles == 1 && (int)grid == g_halo_sm_count && grid % (unsigned)g_halo_cluster == 0) ? (unsigned)g_halo_cluster : 1u;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(HL_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csz;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (csz > 1) {                                             // all clusters must be co-resident (persistent kernel)
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, conv_tc_halo_kernel<BN, UP, C32>, &cfg);
+    if (e != cudaSuccess || max_clusters * (int)csz < (int)grid) {
+      (void)cudaGetLastError();
+      csz = 1;
+      attr[0].val.clusterDim.x = 1;
+    }
+  }
+  const uint8_t* wp = static_cast<const uint8_t*>(wpk);
+  const int total_i = (int)total;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_halo_kernel<BN, UP, C32>, *p, wp, tiles_x, tiles_y, n_tiles, total_i, rjobs, rjob_count);
+  if (le != cudaSuccess) return fail(E4S_ERR_CUDA, "e4s_conv_tc(halo): launch: %s", cudaGetErrorString(le));
   return check_launch("e4s_conv_tc(halo)");
 }
 
@@ -702,7 +780,10 @@ int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4
     case 256: return launch_halo<256, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);     // up: 4 x 256 columns exceed TMEM (geometry_ok)
     case 128: return up ? launch_halo<128, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<128, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
     case 64: return up ? launch_halo<64, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<64, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
-    case 32: return up ? launch_halo<32, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<32, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+    case 32:
+      if (p->cin == 32)
+        return up ? launch_halo<32, true, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<32, false, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
+      return up ? launch_halo<32, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<32, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
     default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc(halo): unsupported cout %d", p->cout);
   }
 }

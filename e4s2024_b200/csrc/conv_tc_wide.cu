@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
     __syncwarp();
   } else {
     // =========================== weight loader =====================================================
-    const int64_t tile_bytes = 2 * (int64_t)bn_packed * 128;
+    // packed chunk (e4s_pack_weights_tc): per (n_tile, kc): [hi tiles of the P phases | lo tiles of the P phases], bn_packed rows each
+    const int64_t t_bytes = (int64_t)bn_packed * 128;
+    const int phases = UP ? 4 : 1;
     int bcount = 0;
     for (int step = 0; step < nsteps; ++step) {
       const int pass = step / num_kc, kc = step - pass * num_kc;
@@ -297,24 +299,22 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
           if (UP) {
             const int cb = (int)blockIdx.y;                            // 128-channel block of this CTA
             const int nt = cb * 128 / bn_packed;
-            const int64_t sub_off = (int64_t)(cb * 128 % bn_packed) * 128;
+            const uint8_t* base = wpk + ((int64_t)nt * num_kc + kc) * (2 * phases * t_bytes) + (int64_t)(cb * 128 % bn_packed) * 128;
             if (mixed) {                                               // one phase: hi 128 rows | lo 128 rows
-              const uint8_t* src = wpk + (((int64_t)pass * nt_packed + nt) * num_kc + kc) * tile_bytes + sub_off;
               mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * WD_SLOT_BYTES);
-              bulk_g2s(dst, src, WD_SLOT_BYTES, bar_bfull + 8 * bs);
-              bulk_g2s(dst + WD_SLOT_BYTES, src + (int64_t)bn_packed * 128, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+              bulk_g2s(dst, base + pass * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+              bulk_g2s(dst + WD_SLOT_BYTES, base + (phases + pass) * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
             } else {                                                   // phases 2sub, 2sub+1: hi hi | lo lo
               mbar_arrive_expect_tx(bar_bfull + 8 * bs, 4 * WD_SLOT_BYTES);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint8_t* src = wpk + (((int64_t)(2 * sub + j) * nt_packed + nt) * num_kc + kc) * tile_bytes + sub_off;
-                bulk_g2s(dst + j * WD_SLOT_BYTES, src, WD_SLOT_BYTES, bar_bfull + 8 * bs);
-                bulk_g2s(dst + (2 + j) * WD_SLOT_BYTES, src + (int64_t)bn_packed * 128, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+                bulk_g2s(dst + j * WD_SLOT_BYTES, base + (2 * sub + j) * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+                bulk_g2s(dst + (2 + j) * WD_SLOT_BYTES, base + (phases + 2 * sub + j) * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
               }
             }
-          } else {                                                     // channels [512*by + 256*sub, +256): one packed 256-row tile
+          } else {                                                     // channels [512*by + 256*sub, +256): one packed 256-row chunk (hi | lo)
             const int nt = (int)blockIdx.y * 2 + sub;
-            const uint8_t* src = wpk + ((int64_t)nt * num_kc + kc) * tile_bytes;
+            const uint8_t* src = wpk + ((int64_t)nt * num_kc + kc) * (2 * t_bytes);
             mbar_arrive_expect_tx(bar_bfull + 8 * bs, 4 * WD_SLOT_BYTES);
             bulk_g2s(dst, src, 4 * WD_SLOT_BYTES, bar_bfull + 8 * bs);
           }

@@ -57,7 +57,7 @@ def halo_geometry_ok(cin: int, cout: int, hin: int, win: int, up2: bool, kh: int
     """Mirror of tc_halo_geometry_ok (conv_tc_halo.cu): what the halo kernel takes."""
     if kh != 3 or stride != 1 or hin % 16 or win % 8:
         return False
-    if not (cin == 32 or cin % 64 == 0):
+    if not ((cin == 32 and cout == 32) or cin % 64 == 0):
         return False
     return (4 if up2 else 1) * min(cout, 256) <= 512 and tc_eligible(cin, cout)
 

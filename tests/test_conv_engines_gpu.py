@@ -35,6 +35,10 @@ CASES = [
     ("halo_up2_c64_n32", 2, 16, 16, 64, 32, 3, 1, True, 1),
     ("halo_up2_c128_n64", 2, 16, 8, 128, 64, 3, 1, True, 1),
     ("halo_up2_c32_n32", 1, 32, 16, 32, 32, 3, 1, True, 1),
+    # halo kernel with a full persistent grid (>= 148 jobs, uneven job counts per CTA): cluster launch, weights multicast
+    ("halo_cluster_c64_n64", 2, 128, 128, 64, 64, 3, 1, False, 1),
+    ("halo_cluster_up2_c64_n32", 2, 128, 128, 64, 32, 3, 1, True, 1),
+    ("halo_cluster_up2_c128_n128", 1, 128, 160, 128, 128, 3, 1, True, 1),
     # geometries taken by the 512-column gather kernel (conv_tc_wide.cu): merged tiles (one region per sample or a coarse
     # mask), mixed tiles (per-pixel random labels -> the four phases of a pixel differ -> per-phase passes)
     ("wide_up2_c128_n128", 2, 16, 16, 128, 128, 3, 1, True, 1),
