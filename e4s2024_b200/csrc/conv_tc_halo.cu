@@ -96,7 +96,7 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint
 template <int BN, bool UP, bool C32>
 __global__ void __launch_bounds__(HL_THREADS, 1)   // 14 warps are allocated as 16: 128 registers per thread is the ceiling
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
-                    const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count) {
+                    const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count, const int bn_packed) {
   constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of one phase of a packed 64-wide K chunk
   constexpr int P = UP ? 4 : 1;
   constexpr int PM = hl_phase_merge(BN, UP);      // phases merged into one MMA (N = PM * BN)
@@ -610,9 +610,18 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               } else {
                 const uint32_t dst = smem_base + B_OFF + bs * STAGE_B;
                 mbar_arrive_expect_tx(bar_bfull + 8 * bs, STAGE_B);
-                // packed chunk (e4s_pack_weights_tc): [hi tiles of the P phases | lo tiles of the P phases]
-                const uint8_t* src = wpk + ((int64_t)jb.nt * num_kc + kc) * (2 * (int64_t)P * B_BYTES);
-                if (mcast) {                                 // this CTA's slice of the stage, to every CTA of the cluster
+                // packed chunk (e4s_pack_weights_tc): [hi tiles of the P phases | lo tiles of the P phases], bn_packed rows each;
+                // BN < bn_packed: this job's n-tile is a 128-row slice of a packed 256-row tile
+                const int64_t tb = (int64_t)bn_packed * 128;
+                const int ch0 = jb.nt * BN;
+                const uint8_t* src = wpk + ((int64_t)(ch0 / bn_packed) * num_kc + kc) * (2 * (int64_t)P * tb) + (int64_t)(ch0 % bn_packed) * 128;
+                if (bn_packed != BN) {                       // sliced tiles: hi and lo of every merged phase separately
+#pragma unroll
+                  for (int q = 0; q < PM; ++q) {
+                    bulk_g2s(dst + q * B_BYTES, src + (int64_t)(pl * PM + q) * tb, B_BYTES, bar_bfull + 8 * bs);
+                    bulk_g2s(dst + (PM + q) * B_BYTES, src + (int64_t)(P + pl * PM + q) * tb, B_BYTES, bar_bfull + 8 * bs);
+                  }
+                } else if (mcast) {                          // this CTA's slice of the stage, to every CTA of the cluster
                   const uint32_t slice = (uint32_t)STAGE_B / csz;
                   if (PM == P) {
                     bulk_g2s_mc(dst + crank * slice, src + crank * slice, slice, bar_bfull + 8 * bs, cmask);
@@ -724,6 +733,7 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
     if (g_halo_sm_count <= 0) g_halo_sm_count = 148;
   }
   const int tiles_x = p->win / HL_TW, tiles_y = p->hin / HL_TH, n_tiles = p->cout / BN;
+  const int bn_packed = tc_block_n(p->cout);                 // row count of the packed weight tiles (e4s_pack_weights_tc)
   const int64_t total = rjobs ? (int64_t)rjob_host_count * n_tiles : (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
   E4S_REQUIRE(total > 0 && total < 0x7fffffff, "conv_tc(halo): bad job count");
   const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
@@ -757,7 +767,7 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
   }
   const uint8_t* wp = static_cast<const uint8_t*>(wpk);
   const int total_i = (int)total;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_halo_kernel<BN, UP, C32>, *p, wp, tiles_x, tiles_y, n_tiles, total_i, rjobs, rjob_count);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_halo_kernel<BN, UP, C32>, *p, wp, tiles_x, tiles_y, n_tiles, total_i, rjobs, rjob_count, bn_packed);
   if (le != cudaSuccess) return fail(E4S_ERR_CUDA, "e4s_conv_tc(halo): launch: %s", cudaGetErrorString(le));
   return check_launch("e4s_conv_tc(halo)");
 }
@@ -777,7 +787,10 @@ int tc_halo_set_trace(void* buf, int cap_records) {
 int tc_launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs, const int* rjob_count, int rjob_host_count) {
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   switch (tc_block_n(p->cout)) {
-    case 256: return launch_halo<256, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);     // up: 4 x 256 columns exceed TMEM (geometry_ok)
+    // cout >= 256: 128-column n-tiles (slices of the packed 256-row tiles).  An M=128 MMA is operand-fetch bound up to
+    // N = 128 (64 cycles) and compute bound at N = 256 (128 cycles): same columns per cycle, but a 64 KB N=256 weight
+    // stage leaves room for ONE stage next to the halo buffers (0.28 ms per 512->512 @32^2 encoder conv, 40 % of its floor)
+    case 256: return launch_halo<128, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);     // up: 4 x 256 columns exceed TMEM (geometry_ok)
     case 128: return up ? launch_halo<128, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<128, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
     case 64: return up ? launch_halo<64, true>(p, wpk, s, rjobs, rjob_count, rjob_host_count) : launch_halo<64, false>(p, wpk, s, rjobs, rjob_count, rjob_host_count);
     case 32:

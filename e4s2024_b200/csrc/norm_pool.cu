@@ -165,16 +165,21 @@ __global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restric
     cnt[j] = 0;
   }
   const float* mb = mask + (int64_t)b * k * mh * mw;
+  // All k mask taps of a pixel are loaded BEFORE any of them is tested: the first version branched on each load
+  // (k dependent L2 round trips per pixel, 1.4 ms per call at 64^2 x 256 channels).  Adding 0.0 for the regions the
+  // pixel is not in keeps the summation order of every (region, channel) sum exactly what it was.
   for (int p = py; p < hw; p += 8) {
     const int y = p / w, xx = p - y * w;
     const int sy = nearest_src(y, mh, h), sx = nearest_src(xx, mw, w);
     const float v = ch < c ? __ldg(feat + ((int64_t)b * hw + p) * f_pitch + ch) : 0.f;
+    float mv[MM_MAXK];
+#pragma unroll
+    for (int j = 0; j < MM_MAXK; ++j) mv[j] = j < k ? __ldg(mb + ((int64_t)j * mh + sy) * mw + sx) : 0.f;
 #pragma unroll
     for (int j = 0; j < MM_MAXK; ++j) {
-      if (j < k && __ldg(mb + ((int64_t)j * mh + sy) * mw + sx) != 0.f) {
-        acc[j] += (double)v;
-        cnt[j] += 1;
-      }
+      const bool in = mv[j] != 0.f;
+      acc[j] += in ? (double)v : 0.0;
+      cnt[j] += in ? 1 : 0;
     }
   }
 #pragma unroll

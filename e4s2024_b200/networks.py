@@ -25,6 +25,15 @@ class LocalMLP(nn.Module):
         self.mlp = nn.Sequential(EqualLinear(dim_component, dim_style // latent_squeeze_ratio, lr_mul=1), nn.LeakyReLU(),
                                  EqualLinear(dim_style // latent_squeeze_ratio, dim_style * num_w_layers, lr_mul=1))
 
+    def rows_deferred(self, src, rows, row_stride, offset, out, extra_bias=None):
+        """The two GEMMs of this MLP as un-launched problems (Net3 batches all 12 MLPs into two launches)."""
+        pw0, b0 = self.mlp[0].packed()
+        h, p0 = E.linear_rows(src, rows, row_stride, offset, pw0, bias=b0, act=L.ACT_LRELU, slope=self.mlp[1].negative_slope,
+                              gain=1.0, launch=False)
+        pw1, b1 = self.mlp[2].packed()
+        _, p1 = E.linear_rows(h, rows, h.shape[1], 0, pw1, bias=b1 if extra_bias is None else extra_bias, out=out, launch=False)
+        return p0, p1, h
+
     def rows(self, src, rows, row_stride, offset, out=None, extra_bias=None):
         pw0, b0 = self.mlp[0].packed()
         h = E.linear_rows(src, rows, row_stride, offset, pw0, bias=b0, act=L.ACT_LRELU, slope=self.mlp[1].negative_slope,
@@ -81,8 +90,15 @@ class Net3(nn.Module):
         codes = torch.empty(b, k, total, 512, device=sv.device, dtype=torch.float32)
         la = self.latent_avg.to(sv.device).float() if add_avg else None
         biases = self._mlp_biases(la, n_mlp_layers) if add_avg else [None] * k
+        # 24 tiny GEMMs (M = batch rows) -> two batched launches (first layers, then second layers)
+        first, second, keep = [], [], []
         for i in range(k):
-            self.MLPs[i].rows(sv, b, k * d, i * d, out=_RowsOut(codes, i, n_mlp_layers), extra_bias=biases[i])
+            p0, p1, h = self.MLPs[i].rows_deferred(sv, b, k * d, i * d, _RowsOut(codes, i, n_mlp_layers), extra_bias=biases[i])
+            first.append(p0)
+            second.append(p1)
+            keep.append(h)
+        L.conv_batched(first)
+        L.conv_batched(second)
         if add_avg and rl != 17:
             codes[:, :, rl:] = la[rl:]
         return codes
