@@ -148,11 +148,13 @@ __global__ void residual_combine_kernel(const float* __restrict__ a, int64_t a_p
 
 constexpr int MM_MAXK = 16;
 
-__global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restrict__ feat, int64_t f_pitch, int h, int w,
-                                                          int c, const float* __restrict__ mask, int k, int mh, int mw,
-                                                          float* __restrict__ codes, int64_t sb, int64_t sk, int c_off) {
-  __shared__ double red[8][32];
-  __shared__ int redc[8];
+constexpr int MM_PY = 16;          // pixel rows per CTA (512 threads): the kernel is a chain of L2 round trips per pixel step
+
+__global__ void __launch_bounds__(32 * MM_PY) masked_mean_kernel(const float* __restrict__ feat, int64_t f_pitch, int h, int w,
+                                                                 int c, const float* __restrict__ mask, int k, int mh, int mw,
+                                                                 float* __restrict__ codes, int64_t sb, int64_t sk, int c_off) {
+  __shared__ double red[MM_PY][32];
+  __shared__ int redc[MM_PY];
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 32, b = blockIdx.y;
   const int ch = c0 + cx;
@@ -165,21 +167,31 @@ __global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restric
     cnt[j] = 0;
   }
   const float* mb = mask + (int64_t)b * k * mh * mw;
-  // All k mask taps of a pixel are loaded BEFORE any of them is tested: the first version branched on each load
-  // (k dependent L2 round trips per pixel, 1.4 ms per call at 64^2 x 256 channels).  Adding 0.0 for the regions the
-  // pixel is not in keeps the summation order of every (region, channel) sum exactly what it was.
-  for (int p = py; p < hw; p += 8) {
-    const int y = p / w, xx = p - y * w;
-    const int sy = nearest_src(y, mh, h), sx = nearest_src(xx, mw, w);
-    const float v = ch < c ? __ldg(feat + ((int64_t)b * hw + p) * f_pitch + ch) : 0.f;
-    float mv[MM_MAXK];
-#pragma unroll
-    for (int j = 0; j < MM_MAXK; ++j) mv[j] = j < k ? __ldg(mb + ((int64_t)j * mh + sy) * mw + sx) : 0.f;
+  // Two pixels per step, all 2k mask taps and both feature values loaded BEFORE any of them is tested: the first
+  // version branched on each mask load (k dependent L2 round trips per pixel, 1.4 ms per call at 64^2 x 256 channels).
+  // Each thread still adds its pixels in increasing order and adding 0.0 for the regions a pixel is not in leaves the sums
+  // unchanged, so the result does not depend on how pixels are grouped into steps.
+  for (int p = py; p < hw; p += 2 * MM_PY) {
+    const int p1 = p + MM_PY;
+    const bool has1 = p1 < hw;
+    const int y0 = p / w, x0 = p - y0 * w;
+    const int y1 = has1 ? p1 / w : y0, x1 = has1 ? p1 - y1 * w : x0;
+    const int sy0 = nearest_src(y0, mh, h), sx0 = nearest_src(x0, mw, w);
+    const int sy1 = nearest_src(y1, mh, h), sx1 = nearest_src(x1, mw, w);
+    const float v0 = ch < c ? __ldg(feat + ((int64_t)b * hw + p) * f_pitch + ch) : 0.f;
+    const float v1 = (ch < c && has1) ? __ldg(feat + ((int64_t)b * hw + p1) * f_pitch + ch) : 0.f;
+    float m0[MM_MAXK], m1[MM_MAXK];
 #pragma unroll
     for (int j = 0; j < MM_MAXK; ++j) {
-      const bool in = mv[j] != 0.f;
-      acc[j] += in ? (double)v : 0.0;
-      cnt[j] += in ? 1 : 0;
+      m0[j] = j < k ? __ldg(mb + ((int64_t)j * mh + sy0) * mw + sx0) : 0.f;
+      m1[j] = (j < k && has1) ? __ldg(mb + ((int64_t)j * mh + sy1) * mw + sx1) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < MM_MAXK; ++j) {
+      const bool in0 = m0[j] != 0.f, in1 = m1[j] != 0.f;
+      acc[j] += in0 ? (double)v0 : 0.0;
+      acc[j] += in1 ? (double)v1 : 0.0;
+      cnt[j] += (in0 ? 1 : 0) + (in1 ? 1 : 0);
     }
   }
 #pragma unroll
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restric
       double s = 0.0;
       int n = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MM_PY; ++i) {
         s += red[i][cx];
         n += redc[i];
       }
@@ -289,7 +301,7 @@ extern "C" int e4s_masked_mean_f32(const float* feat, int64_t f_pitch, int batch
   E4S_REQUIRE(feat && mask && codes && batch > 0 && h > 0 && w > 0 && c > 0, "masked_mean: bad args");
   E4S_REQUIRE(k > 0 && k <= MM_MAXK && mh > 0 && mw > 0, "masked_mean: k must be in 1..%d", MM_MAXK);
   dim3 grid(ceil_div(c, 32), batch);
-  masked_mean_kernel<<<grid, 256, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, mask, k, mh, mw, codes, codes_stride_b,
+  masked_mean_kernel<<<grid, 32 * MM_PY, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, mask, k, mh, mw, codes, codes_stride_b,
                                                          codes_stride_k, c_off);
   return check_launch("masked_mean");
 }
