@@ -74,6 +74,59 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bench_config(world, engine="tc"):
+    """`config` of the JSON line: the same dict for both arms (the reference arm adds what its bounded sample was)."""
+    return {"workload": "configs[1]: batch=16/GPU 1024x1024 StyleGAN2 regional synthesis from random regional style codes",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * world, "size": SIZE, "regions": K, "remaining_layer_idx": RL,
+            "masks": "blocky one-hot 32x32 cells @512^2", "noise": "registered buffers (randomize_noise=False)",
+            "parallelism": f"batch-sharded x{world}" + (" + NCCL all_gather of images" if world > 1 else ""),
+            "conv_engine": engine, "l2": "working set (>2 GB activations per step) exceeds the 126 MB L2"}
+
+
+def swap_path_line(dev, steps=3):
+    """BASELINE.json's metric names the whole swap hot path (parsing + encoder + synthesis, configs[4] per GPU shard):
+    FaceParser.parse_batch -> one-hot -> Net3.forward at 16 faces, inputs resident, CUDA events, stage by stage."""
+    from e4s2024_b200 import _lib as L, synth
+    from e4s2024_b200.face_parsing.face_parsing_demo import FaceParser
+    from e4s2024_b200.networks import Net3
+    import types
+    # the fields Net3 reads from the reference's option object (options/our_swap_face_pipeline_options.py:12-18,50)
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=RL, num_seg_cls=K, out_size=SIZE, train_G=False,
+                                 start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts)
+    synth.synth_module_weights(net, seed=9)
+    net = net.to(dev)
+    net.latent_avg = synth.randn("net3.latent_avg", (18, 512), 9, 0.1).to(dev)
+    parser = FaceParser(seg_ckpt=None, size=SIZE, device=str(dev))
+    synth.synth_module_weights(parser.seg, seed=10)
+    parser.seg.to(dev)
+    img = synth.smooth_image("swap.img", BATCH, SIZE, 13).to(dev)
+    img01 = (img + 1) / 2
+
+    def t(fn):
+        r = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, r
+
+    ms_parse, lab = t(lambda: parser.parse_batch(img01))
+    ms_onehot, mask = t(lambda: L.labels_to_onehot(lab, K))
+    ms_enc, (vec, _) = t(lambda: net.get_style_vectors(img, mask))
+    ms_codes, codes = t(lambda: net.cal_style_codes(vec))
+    ms_gen, _ = t(lambda: net.gen_img(None, codes, mask, randomize_noise=False))
+    ms_all, _ = t(lambda: net(img, L.labels_to_onehot(parser.parse_batch(img01), K), randomize_noise=False))
+    del net, parser
+    return {"workload": "configs[4] per-GPU shard: 16 faces, bicubic 1024->512 + BiSeNet + argmax/LUT -> one-hot -> Net3 (encoder, 12 MLPs, generator)",
+            "value": BATCH / ms_all * 1e3, "unit": "faces/s", "ms_per_step": ms_all,
+            "stage_ms": {"parse": ms_parse, "onehot": ms_onehot, "encoder": ms_enc, "mlps": ms_codes, "generator": ms_gen},
+            "alg_gflop_per_face": 405.5, "note": "BiSeNet runs on the exact-fp32 CUDA-core engine (bit-exact label maps), the rest on tcgen05"}
+
+
 def make_generator_inputs(batch, seed=1):
     from e4s2024_b200 import synth
     latent = synth.randn("bench.latent", (batch, K, 18, 512), seed)
@@ -123,8 +176,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = {"workload": "configs[1]: StyleGAN2 regional synthesis 1024^2, K=12, rl=13 (CPU reference algorithm)",
-           "batch_per_step": 1, "size": SIZE}
+    cfg = bench_config(max(int(os.environ.get("WORLD_SIZE", "1")), 1), engine="cpu")
+    cfg["sample"] = "1 face per step (bounded sample of the 16-face batch), CPU reference algorithm, all host threads that help"
     from e4s2024_b200 import synth
     from e4s2024_b200.stylegan2.model import generator_state_shapes
     from oracle import e4s_oracle as orc
@@ -165,6 +218,7 @@ def main():
     ap.add_argument("--impl", default="e4s_b200", choices=["e4s_b200", "reference"])
     ap.add_argument("--engine", default=None, choices=[None, "tc", "f32"], help="conv engine override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-swap-path", action="store_true", help="skip the full swap-path (parser + encoder + generator) timing")
     ap.add_argument("--dump-layers", default=None, help="write per-conv-launch timings (JSON lines) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -275,8 +329,12 @@ def main():
     if dom:
         d = by[dom]
         ach = d["alg"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 bf16x3)" if dom == "tc" else "conv_igemm_f32_kernel (CUDA-core fp32)",
-                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")       # dram bytes of the same 17 launches, one ncu --set full capture
+        if dom == "tc" and os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_step")
+        roof = {"bound": "tensor", "kernel": "conv_tc_{halo,wide,gather} kernels (tcgen05 bf16x3), the 17 convolution launches of one step" if dom == "tc" else "conv_igemm_f32_kernel (CUDA-core fp32)",
+                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic,
                 "peak_source": pk["source"], "launches": d["n"], "kernel_ms_per_step": d["ms"],
                 "executed_tflops": d["exec"] / (d["ms"] * 1e-3) / 1e12,
                 "note": "achieved = algorithmic conv FLOPs (each output pixel once, conv_transpose at input resolution) / summed "
@@ -284,23 +342,24 @@ def main():
                         "the poly-phase up-convs execute 4x the algorithmic MACs (executed_tflops counts the latter, not the split)",
                 "by_engine": {k: {"ms": v["ms"], "launches": v["n"], "alg_tflops": v["alg"] / (v["ms"] * 1e-3) / 1e12} for k, v in by.items()}}
 
+    swap = None
+    if rank == 0 and world == 1 and not args.no_swap_path:
+        del G, pipe
+        torch.cuda.empty_cache()
+        swap = swap_path_line(dev)
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline()
         line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if E.conv_engine() == "tc" else "f32",
                 "data": "synthetic",
-                "config": {"workload": "configs[1]: batch=16/GPU 1024x1024 StyleGAN2 regional synthesis from random regional style codes",
-                           "batch_per_gpu": BATCH, "global_batch": BATCH * world, "size": SIZE, "regions": K, "remaining_layer_idx": RL,
-                           "masks": "blocky one-hot 32x32 cells @512^2", "noise": "registered buffers (randomize_noise=False)",
-                           "parallelism": f"batch-sharded x{world}" + (" + NCCL all_gather of images" if world > 1 else ""),
-                           "conv_engine": E.conv_engine(), "l2": "working set (>2 GB activations per step) exceeds the 126 MB L2"},
+                "config": bench_config(world, E.conv_engine()),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e / args.steps,
                         "note": "Generator.forward through HostPipeline: pinned-host H2D of every step's latent+mask and D2H of its images, "
                                 "double-buffered on copy streams (timed region = first H2D to last D2H complete)",
                         "h2d_bytes_per_step": int(latent_h.numel() * 4 + mask_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "swap_path": swap,
                 "alg_gflop_per_face": ALG_GFLOP_PER_FACE,
                 "job_alg_tflops": value * ALG_GFLOP_PER_FACE / 1e3}
         print(json.dumps(line))
