@@ -226,42 +226,66 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
   const int hw = h * w;
   const int64_t tile0 = (int64_t)blockIdx.x * TORGB_TILE;
   // ---- phase A: dot products ---------------------------------------------------------------------
-  for (int t = warp * PPW + sub; t < TORGB_TILE; t += 8 * PPW) {       // whole warp iterates together (t differs by sub only)
-    const int64_t pix = tile0 + t;
-    const bool ok = pix < npix;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (ok) {
-      const int b = (int)(pix / hw);
-      int r = 0;
-      if (labels) {
-        const int rem = (int)(pix - (int64_t)b * hw);
-        const int y = rem / w, xx = rem - y * w;
-        r = labels[((int64_t)b * lab_h + nearest_src(y, lab_h, h)) * lab_w + nearest_src(xx, lab_w, w)];
+  // TU pixels per warp step with independent accumulators: every step is a chain of dependent global loads (label ->
+  // style row -> features), and one pixel per step made the kernel pure latency (90 us per launch whatever the grid size).
+  constexpr int TU = 4;
+  for (int t0 = warp * PPW + sub; t0 < TORGB_TILE; t0 += 8 * PPW * TU) {       // whole warp iterates together (t differs by sub only)
+    float a0[TU], a1[TU], a2[TU];
+    const float* xr[TU];
+    const float* sr[TU];
+    bool ok[TU];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const int t = t0 + u * 8 * PPW;
+      const int64_t pix = tile0 + t;
+      a0[u] = a1[u] = a2[u] = 0.f;
+      ok[u] = t < TORGB_TILE && pix < npix;
+      xr[u] = x;
+      sr[u] = smod;
+      if (ok[u]) {
+        const int b = (int)(pix / hw);
+        int r = 0;
+        if (labels) {
+          const int rem = (int)(pix - (int64_t)b * hw);
+          const int y = rem / w, xx = rem - y * w;
+          r = labels[((int64_t)b * lab_h + nearest_src(y, lab_h, h)) * lab_w + nearest_src(xx, lab_w, w)];
+        }
+        xr[u] = x + pix * x_pitch;
+        sr[u] = smod + ((int64_t)b * regions + r) * cin;
       }
-      const float* xr = x + pix * x_pitch;
-      const float* sr = smod + ((int64_t)b * regions + r) * cin;
-      for (int ci = ll * 4; ci < cin; ci += LP * 4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(xr + ci));
-        const float4 sm = __ldg(reinterpret_cast<const float4*>(sr + ci));
-        v.x *= sm.x; v.y *= sm.y; v.z *= sm.z; v.w *= sm.w;
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrgb + ci));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci));
-        const float4 w2 = __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci));
-        a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
-        a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
-        a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+    }
+    for (int ci = ll * 4; ci < cin; ci += LP * 4) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrgb + ci));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci));
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci));
+      float4 v[TU], sm[TU];
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
+        v[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(xr[u] + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sm[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(sr[u] + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
+        v[u].x *= sm[u].x; v[u].y *= sm[u].y; v[u].z *= sm[u].z; v[u].w *= sm[u].w;
+        a0[u] += v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
+        a1[u] += v[u].x * w1.x + v[u].y * w1.y + v[u].z * w1.z + v[u].w * w1.w;
+        a2[u] += v[u].x * w2.x + v[u].y * w2.y + v[u].z * w2.z + v[u].w * w2.w;
       }
     }
 #pragma unroll
-    for (int o = LP / 2; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (ll == 0) {
-      srgb[0][t] = a0;
-      srgb[1][t] = a1;
-      srgb[2][t] = a2;
+    for (int u = 0; u < TU; ++u) {
+#pragma unroll
+      for (int o = LP / 2; o > 0; o >>= 1) {
+        a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
+        a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
+        a2[u] += __shfl_xor_sync(0xffffffffu, a2[u], o);
+      }
+      const int t = t0 + u * 8 * PPW;
+      if (ll == 0 && t < TORGB_TILE) {
+        srgb[0][t] = a0[u];
+        srgb[1][t] = a1[u];
+        srgb[2][t] = a2[u];
+      }
     }
   }
   __syncthreads();
