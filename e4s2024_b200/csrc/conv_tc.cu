@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     er.nw = p.noise ? __ldg(p.noise_w) : 0.f;
     er.nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
     er.nz = (er.nrow && p.noise_sc == 0) ? er.nw * __ldg(er.nrow) : 0.f;
-    if (tc_epi_is_fast(p)) {
+    E4SConv pf = p;                          // the fast form also covers a residual added before the activation (ResNet blocks)
+    pf.res = nullptr;
+    if (tc_epi_is_fast(pf) && !(p.res && p.res_after_act)) {
       // branch-free epilogue (tc_ptx.cuh): per-row demodulation from global memory (rows of a tile may belong to different
       // regions), the layer-wide bias / slope vectors through a 16-column register block
       const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
@@ -281,6 +283,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
           }
           add[qd] = p.ch_shift ? ldg4(p.ch_shift + n) : make_float4(0.f, 0.f, 0.f, 0.f);
           sl[qd] = make_float4(tc_epi_slope(p, n), tc_epi_slope(p, n + 1), tc_epi_slope(p, n + 2), tc_epi_slope(p, n + 3));
+        }
+        if (p.res && live) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 rv = ldg4(p.res + pix * p.res_pitch + n_base + c0 + 4 * qd);
+            add[qd].x += rv.x; add[qd].y += rv.y; add[qd].z += rv.z; add[qd].w += rv.w;
+          }
         }
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
         if (live) {
