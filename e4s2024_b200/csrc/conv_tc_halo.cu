@@ -737,11 +737,13 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
   const int64_t total = rjobs ? (int64_t)rjob_host_count * n_tiles : (int64_t)p->batch * tiles_x * tiles_y * n_tiles;
   E4S_REQUIRE(total > 0 && total < 0x7fffffff, "conv_tc(halo): bad job count");
   const unsigned grid = (unsigned)(total < g_halo_sm_count ? total : g_halo_sm_count);
-  // cluster size for the weight multicast (E4S_HALO_CLUSTER = 1 | 2 | 4, default 2): full persistent grids with one n-tile only
+  // cluster size for the weight multicast (E4S_HALO_CLUSTER = 1 | 2 | 4): full persistent grids with one n-tile only.
+  // Default 1: measured on B200 the multicast changes nothing (the layers are bound by shared-memory bandwidth inside the
+  // SM, not by L2->SM traffic), so the plain launch is kept as the production path.
   if (g_halo_cluster < 0) {
     const char* e = getenv("E4S_HALO_CLUSTER");
-    g_halo_cluster = e ? atoi(e) : 2;
-    if (g_halo_cluster != 1 && g_halo_cluster != 2 && g_halo_cluster != 4) g_halo_cluster = 2;
+    g_halo_cluster = e ? atoi(e) : 1;
+    if (g_halo_cluster != 1 && g_halo_cluster != 2 && g_halo_cluster != 4) g_halo_cluster = 1;
   }
   unsigned csz = (n_tiles == 1 && (int)grid == g_halo_sm_count && grid % (unsigned)g_halo_cluster == 0) ? (unsigned)g_halo_cluster : 1u;
   cudaLaunchConfig_t cfg{};
