@@ -42,6 +42,7 @@ class E4SConv(C.Structure):
         ("act", _i32), ("act_slope", _f32), ("act_gain", _f32), ("act_prelu", _fp),
         ("out", _fp), ("out_pitch", _i64), ("accumulate", _i32),
         ("rgb", _fp), ("rgb_w", _fp), ("rgb_smod", _fp), ("rgb_bias", _fp), ("rgb_skip", _fp), ("rgb_fir", _fp),
+        ("pred_count", _fp), ("pred_limit", _i32), ("pred_run_if_gt", _i32),
     ]
 
 

@@ -33,6 +33,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope, float 
 template <int BN>
 __device__ __forceinline__ void conv_igemm_f32_body(const E4SConv& p, const int64_t m_total, const int bx, const int by, const int phase) {
   constexpr int NH = BN / 64;  // column halves handled per thread (4 columns each)
+  if (p.pred_count != nullptr && ((__ldg(p.pred_count) > p.pred_limit) != (p.pred_run_if_gt != 0))) return;   // device-side launch predicate (e4s_b200.h)
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + APAD];
   __shared__ Row rows[BM];

@@ -32,6 +32,7 @@ struct TcRow {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int64_t m_total,
                                                                   const int tile2d) {
+  if (p.pred_count != nullptr && ((__ldg(p.pred_count) > p.pred_limit) != (p.pred_run_if_gt != 0))) return;   // device-side launch predicate (e4s_b200.h)
   constexpr int STAGES = tc_stages(BN);
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BN);

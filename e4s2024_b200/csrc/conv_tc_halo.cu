@@ -97,6 +97,7 @@ template <int BN, bool UP, bool C32>
 __global__ void __launch_bounds__(HL_THREADS, 1)   // 14 warps are allocated as 16: 128 registers per thread is the ceiling
 conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int tiles_x, const int tiles_y, const int n_tiles,
                     const int total_jobs_in, const int4* __restrict__ rjobs, const int* __restrict__ rjob_count, const int bn_packed) {
+  if (p.pred_count != nullptr && ((__ldg(p.pred_count) > p.pred_limit) != (p.pred_run_if_gt != 0))) return;   // device-side launch predicate (e4s_b200.h)
   constexpr int B_BYTES = BN * 128;               // one bf16 weight tile (hi or lo) of one phase of a packed 64-wide K chunk
   constexpr int P = UP ? 4 : 1;
   constexpr int PM = hl_phase_merge(BN, UP);      // phases merged into one MMA (N = PM * BN)

@@ -36,21 +36,34 @@ struct WdRow {
   uint32_t r4;        // region of the row's output pixel per slot, one byte each
 };
 
-template <bool UP>
+// PAIR = true: launched as clusters of two CTAs (adjacent tiles, same channel block) that execute ONE cta_group::2 MMA
+// (M = 256): each CTA gathers its own A tile and loads HALF of every B sub-step (its 128 of the 256 rows), so the weight
+// bytes written to and read from each SM's shared memory halve.  The 1-CTA kernel needs ~147 B/cycle of shared-memory
+// traffic at full MMA rate (A 4 KB + B 8 KB read per 128-cycle MMA, B 64 KB written per 1536 cycles) against 128
+// available and sits at 62-71 % tensor-pipe-active; the pair needs ~94.  Rank 0 issues every MMA; rank 1's MMA warp
+// relays "my A / B stage is full" to rank 0; stage releases and the accumulator barrier are multicast commits.
+template <bool UP, bool PAIR>
 __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int bn_packed,
                                                                      const int nt_packed) {
+  if (p.pred_count != nullptr && ((__ldg(p.pred_count) > p.pred_limit) != (p.pred_run_if_gt != 0))) return;   // device-side launch predicate (e4s_b200.h)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   constexpr int B_OFF = WD_A_STAGES * WD_A_STAGE;
   WdRow* rows = reinterpret_cast<WdRow*>(smem + B_OFF + WD_B_STAGES * WD_B_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF + WD_B_STAGES * WD_B_STAGE + TC_BM * 16);
+  constexpr int NB = PAIR ? 4 : 2;                    // B ring stages (pair: half-size stages, twice as many)
+  constexpr int BSTAGE = PAIR ? WD_B_STAGE / 2 : WD_B_STAGE;
   const uint32_t bar_afull = smem_u32(bars);          // 2
   const uint32_t bar_aempty = bar_afull + 16;         // 2
-  const uint32_t bar_bfull = bar_aempty + 16;         // 2
-  const uint32_t bar_bempty = bar_bfull + 16;         // 2
-  const uint32_t bar_acc = bar_bempty + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const uint32_t bar_bfull = bar_aempty + 16;         // up to 4
+  const uint32_t bar_bempty = bar_bfull + 32;         // up to 4
+  const uint32_t bar_acc = bar_bempty + 32;
+  const uint32_t bar_pafull = bar_acc + 8;            // 2: peer's A stage is full (pair, rank 0 only)
+  const uint32_t bar_pbfull = bar_pafull + 16;        // 4: peer's B stage is full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint32_t* pair_flag = tmem_slot + 1;                // this CTA's "tile has mixed rows" flag, read by the peer
+  const uint32_t crank = PAIR ? cluster_rank() : 0u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kc = 9 * p.cin / 64;                  // cin % 64 == 0: chunk = (64-channel group, tap), group outer
@@ -88,16 +101,28 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_afull + 8 * s, TC_PRODUCER_WARPS);
       mbar_init(bar_aempty + 8 * s, 1);
+      mbar_init(bar_pafull + 8 * s, 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
       mbar_init(bar_bempty + 8 * s, 1);
+      mbar_init(bar_pbfull + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == TC_PRODUCER_WARPS) {
+    if (PAIR) tmem_alloc2(smem_u32(tmem_slot), 512);
+    else tmem_alloc(smem_u32(tmem_slot), 512);
+  }
   tc_fence_before();
-  const int mixed = __syncthreads_or(mixed_row);       // any row whose four phases straddle a region boundary
+  int mixed = __syncthreads_or(mixed_row);             // any row whose four phases straddle a region boundary
+  if (PAIR) {                                          // both CTAs of a pair must walk the same step sequence
+    if (tid == 0) *pair_flag = (uint32_t)mixed;
+    cluster_sync_all();                                // also: barrier inits visible to the peer before any remote arrive / multicast commit
+    mixed |= (int)ld_shared_cluster_u32(mapa_u32(smem_u32(pair_flag), crank ^ 1u));
+  }
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
   const int npass = mixed ? 4 : 1;                     // mixed tile: one pass per phase, N = 128
@@ -238,51 +263,98 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
   } else if (warp == TC_PRODUCER_WARPS) {
     // =========================== MMA issuer ========================================================
     constexpr uint32_t D_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);    // SBO 1024, version 1, SWIZZLE_128B
-    const uint32_t idesc = umma_idesc(mixed ? 128 : 256);
-    const uint32_t lo_off = (uint32_t)((mixed ? 1 : 2) * WD_SLOT_BYTES) >> 4;     // B_lo follows the N rows of B_hi
+    const int nmma = mixed ? 128 : 256;                                            // N of one MMA
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    // B_lo follows this CTA's rows of B_hi (pair: half of the MMA's N rows live in each CTA)
+    const uint32_t lo_off = (uint32_t)((nmma / (PAIR ? 2 : 1)) * 128) >> 4;
     int bcount = 0;
-    for (int step = 0; step < nsteps; ++step) {
-      const int s = step & 1;
-      const int pass = step / num_kc, kc = step - pass * num_kc;
-      mbar_wait(bar_afull + 8 * s, (step >> 1) & 1);
-      tc_fence_after();
-      const uint32_t a_h = (((smem_base + s * WD_A_STAGE) >> 4) & 0x3FFFu) | (1u << 16), a_l = a_h + (TC_A_BYTES >> 4);
-      for (int sub = 0; sub < nsub; ++sub, ++bcount) {
-        const int bs = bcount & 1;
-        mbar_wait(bar_bfull + 8 * bs, (bcount >> 1) & 1);
-        tc_fence_after();
-        const uint32_t b_h = (((smem_base + B_OFF + bs * WD_B_STAGE) >> 4) & 0x3FFFu) | (1u << 16), b_l = b_h + lo_off;
-        const uint32_t tacc = tmem_acc + (uint32_t)(mixed ? pass * 128 : sub * 256);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t first = (uint32_t)((kc | k) != 0);
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p, t;\n\t"
-                ".reg .b64 dah, dal, dbh, dbl;\n\t"
-                "setp.ne.b32 p, %6, 0;\n\t"
-                "setp.eq.b32 t, 0, 0;\n\t"
-                "mov.b64 dah, {%1, %5};\n\t"
-                "mov.b64 dal, {%2, %5};\n\t"
-                "mov.b64 dbh, {%3, %5};\n\t"
-                "mov.b64 dbl, {%4, %5};\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %7, p;\n\t"      // small terms first
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %7, t;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %7, t;\n\t"
-                "}" ::"r"(tacc),
-                "r"(a_h + 2 * k), "r"(a_l + 2 * k), "r"(b_h + 2 * k), "r"(b_l + 2 * k), "r"(D_HI), "r"(first), "r"(idesc)
-                : "memory");
+    if (PAIR && crank != 0) {
+      // rank 1: relay "stage full" to rank 0 (its producers / loader only signal their own CTA's barriers)
+      if (elect_one()) {
+        for (int step = 0; step < nsteps; ++step) {
+          const int s = step & 1;
+          mbar_wait(bar_afull + 8 * s, (step >> 1) & 1);
+          mbar_arrive_remote(mapa_u32(bar_pafull + 8 * s, 0));
+          for (int sub = 0; sub < nsub; ++sub, ++bcount) {
+            const int bs = bcount % NB;
+            mbar_wait(bar_bfull + 8 * bs, (bcount / NB) & 1);
+            mbar_arrive_remote(mapa_u32(bar_pbfull + 8 * bs, 0));
           }
-          umma_commit(bar_bempty + 8 * bs);
+        }
+      }
+      __syncwarp();
+    } else {
+      for (int step = 0; step < nsteps; ++step) {
+        const int s = step & 1;
+        const int pass = step / num_kc, kc = step - pass * num_kc;
+        mbar_wait(bar_afull + 8 * s, (step >> 1) & 1);
+        if (PAIR) mbar_wait_cluster(bar_pafull + 8 * s, (step >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_h = (((smem_base + s * WD_A_STAGE) >> 4) & 0x3FFFu) | (1u << 16), a_l = a_h + (TC_A_BYTES >> 4);
+        for (int sub = 0; sub < nsub; ++sub, ++bcount) {
+          const int bs = bcount % NB;
+          mbar_wait(bar_bfull + 8 * bs, (bcount / NB) & 1);
+          if (PAIR) mbar_wait_cluster(bar_pbfull + 8 * bs, (bcount / NB) & 1);
+          tc_fence_after();
+          const uint32_t b_h = (((smem_base + B_OFF + bs * BSTAGE) >> 4) & 0x3FFFu) | (1u << 16), b_l = b_h + lo_off;
+          const uint32_t tacc = tmem_acc + (uint32_t)(mixed ? pass * 128 : sub * 256);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t first = (uint32_t)((kc | k) != 0);
+              if (PAIR) {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p, t;\n\t"
+                    ".reg .b64 dah, dal, dbh, dbl;\n\t"
+                    "setp.ne.b32 p, %6, 0;\n\t"
+                    "setp.eq.b32 t, 0, 0;\n\t"
+                    "mov.b64 dah, {%1, %5};\n\t"
+                    "mov.b64 dal, {%2, %5};\n\t"
+                    "mov.b64 dbh, {%3, %5};\n\t"
+                    "mov.b64 dbl, {%4, %5};\n\t"
+                    "tcgen05.mma.cta_group::2.kind::f16 [%0], dal, dbh, %7, p;\n\t"      // small terms first
+                    "tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbl, %7, t;\n\t"
+                    "tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbh, %7, t;\n\t"
+                    "}" ::"r"(tacc),
+                    "r"(a_h + 2 * k), "r"(a_l + 2 * k), "r"(b_h + 2 * k), "r"(b_l + 2 * k), "r"(D_HI), "r"(first), "r"(idesc)
+                    : "memory");
+              } else {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p, t;\n\t"
+                    ".reg .b64 dah, dal, dbh, dbl;\n\t"
+                    "setp.ne.b32 p, %6, 0;\n\t"
+                    "setp.eq.b32 t, 0, 0;\n\t"
+                    "mov.b64 dah, {%1, %5};\n\t"
+                    "mov.b64 dal, {%2, %5};\n\t"
+                    "mov.b64 dbh, {%3, %5};\n\t"
+                    "mov.b64 dbl, {%4, %5};\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %7, p;\n\t"      // small terms first
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %7, t;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %7, t;\n\t"
+                    "}" ::"r"(tacc),
+                    "r"(a_h + 2 * k), "r"(a_l + 2 * k), "r"(b_h + 2 * k), "r"(b_l + 2 * k), "r"(D_HI), "r"(first), "r"(idesc)
+                    : "memory");
+              }
+            }
+            if (PAIR) umma_commit_mc2(bar_bempty + 8 * bs, 3);
+            else umma_commit(bar_bempty + 8 * bs);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          if (PAIR) umma_commit_mc2(bar_aempty + 8 * s, 3);
+          else umma_commit(bar_aempty + 8 * s);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(bar_aempty + 8 * s);
+      if (elect_one()) {
+        if (PAIR) umma_commit_mc2(bar_acc, 3);
+        else umma_commit(bar_acc);
+      }
       __syncwarp();
     }
-    if (elect_one()) umma_commit(bar_acc);
-    __syncwarp();
   } else {
     // =========================== weight loader =====================================================
     // packed chunk (e4s_pack_weights_tc): per (n_tile, kc): [hi tiles of the P phases | lo tiles of the P phases], bn_packed rows each
@@ -292,15 +364,27 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
     for (int step = 0; step < nsteps; ++step) {
       const int pass = step / num_kc, kc = step - pass * num_kc;
       for (int sub = 0; sub < nsub; ++sub, ++bcount) {
-        const int bs = bcount & 1;
-        mbar_wait(bar_bempty + 8 * bs, ((bcount >> 1) & 1) ^ 1);
-        const uint32_t dst = smem_base + B_OFF + bs * WD_B_STAGE;
+        const int bs = bcount % NB;
+        mbar_wait(bar_bempty + 8 * bs, ((bcount / NB) & 1) ^ 1);
+        const uint32_t dst = smem_base + B_OFF + bs * BSTAGE;
         if (elect_one()) {
           if (UP) {
-            const int cb = (int)blockIdx.y;                            // 128-channel block of this CTA
+            const int cb = (int)blockIdx.y;                            // 128-channel block of this CTA (pair)
             const int nt = cb * 128 / bn_packed;
             const uint8_t* base = wpk + ((int64_t)nt * num_kc + kc) * (2 * phases * t_bytes) + (int64_t)(cb * 128 % bn_packed) * 128;
-            if (mixed) {                                               // one phase: hi 128 rows | lo 128 rows
+            if (PAIR) {
+              if (mixed) {                                             // phase `pass`, this CTA's 64 of the 128 channels: hi | lo
+                const int64_t roff = (int64_t)crank * 64 * 128;
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, WD_SLOT_BYTES);
+                bulk_g2s(dst, base + pass * t_bytes + roff, WD_SLOT_BYTES / 2, bar_bfull + 8 * bs);
+                bulk_g2s(dst + WD_SLOT_BYTES / 2, base + (phases + pass) * t_bytes + roff, WD_SLOT_BYTES / 2, bar_bfull + 8 * bs);
+              } else {                                                 // this CTA's phase of the pair (2sub + rank): hi | lo
+                const int ph = 2 * sub + (int)crank;
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * WD_SLOT_BYTES);
+                bulk_g2s(dst, base + ph * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+                bulk_g2s(dst + WD_SLOT_BYTES, base + (phases + ph) * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+              }
+            } else if (mixed) {                                        // one phase: hi 128 rows | lo 128 rows
               mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * WD_SLOT_BYTES);
               bulk_g2s(dst, base + pass * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
               bulk_g2s(dst + WD_SLOT_BYTES, base + (phases + pass) * t_bytes, WD_SLOT_BYTES, bar_bfull + 8 * bs);
@@ -315,8 +399,15 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
           } else {                                                     // channels [512*by + 256*sub, +256): one packed 256-row chunk (hi | lo)
             const int nt = (int)blockIdx.y * 2 + sub;
             const uint8_t* src = wpk + ((int64_t)nt * num_kc + kc) * (2 * t_bytes);
-            mbar_arrive_expect_tx(bar_bfull + 8 * bs, 4 * WD_SLOT_BYTES);
-            bulk_g2s(dst, src, 4 * WD_SLOT_BYTES, bar_bfull + 8 * bs);
+            if (PAIR) {                                                // this CTA's 128 of the 256 rows: hi | lo
+              const int64_t roff = (int64_t)crank * WD_SLOT_BYTES;
+              mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * WD_SLOT_BYTES);
+              bulk_g2s(dst, src + roff, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+              bulk_g2s(dst + WD_SLOT_BYTES, src + t_bytes + roff, WD_SLOT_BYTES, bar_bfull + 8 * bs);
+            } else {
+              mbar_arrive_expect_tx(bar_bfull + 8 * bs, 4 * WD_SLOT_BYTES);
+              bulk_g2s(dst, src, 4 * WD_SLOT_BYTES, bar_bfull + 8 * bs);
+            }
           }
         }
         __syncwarp();
@@ -325,9 +416,11 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
   }
 
   __syncthreads();
+  if (PAIR) cluster_sync_all();                        // the peer may still be reading this CTA's operands / accumulating into its TMEM
   if (warp == TC_PRODUCER_WARPS) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, 512);
+    if (PAIR) tmem_dealloc2(tmem_acc, 512);
+    else tmem_dealloc(tmem_acc, 512);
   }
 }
 
@@ -345,11 +438,16 @@ bool tc_wide_eligible(const E4SConv* p) {
   return up ? (p->cout % 128 == 0) : (p->cout % 512 == 0);
 }
 
-template <bool UP>
+// -1: read E4S_TC_WIDE_PAIR.  Default OFF: the cta_group::2 variant is correct (same tests) but measured 2-7 % SLOWER than
+// the 1-CTA kernel on every wide layer (profiles/r1_layers_v12_pair.jsonl) -- the 1-CTA kernel already runs at the
+// sustained (power-limited) bf16 rate cuBLAS reaches on this part, so halving the per-SM weight traffic buys nothing.
+static int g_wide_pair = -1;
+
+template <bool UP, bool PAIR>
 static int launch_wide_t(const E4SConv* p, const void* wpk, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_wide_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_wide_kernel<UP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM);
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(wide): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -357,13 +455,35 @@ static int launch_wide_t(const E4SConv* p, const void* wpk, cudaStream_t s) {
   const int64_t tiles = (int64_t)p->batch * (gh / 16) * (gw / 8);
   E4S_REQUIRE(tiles > 0 && tiles < 0x7fffffff, "conv_tc(wide): bad tile count");
   const int bn = tc_block_n(p->cout);
-  dim3 grid((unsigned)tiles, (unsigned)(UP ? p->cout / 128 : p->cout / 512), 1);
-  conv_tc_wide_kernel<UP><<<grid, WD_THREADS, WD_SMEM, s>>>(*p, static_cast<const uint8_t*>(wpk), bn, p->cout / bn);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)tiles, (unsigned)(UP ? p->cout / 128 : p->cout / 512), 1);
+  cfg.blockDim = dim3(WD_THREADS);
+  cfg.dynamicSmemBytes = WD_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint8_t* wp = static_cast<const uint8_t*>(wpk);
+  const int ntp = p->cout / bn;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_wide_kernel<UP, PAIR>, *p, wp, bn, ntp);
+  if (le != cudaSuccess) return fail(E4S_ERR_CUDA, "e4s_conv_tc(wide): launch: %s", cudaGetErrorString(le));
   return check_launch("e4s_conv_tc(wide)");
 }
 
 int tc_launch_wide(const E4SConv* p, const void* wpk, cudaStream_t s) {
-  return p->mode == E4S_CONV_UP2_POLYPHASE ? launch_wide_t<true>(p, wpk, s) : launch_wide_t<false>(p, wpk, s);
+  if (g_wide_pair < 0) {
+    const char* e = getenv("E4S_TC_WIDE_PAIR");
+    g_wide_pair = (e && e[0] == '1') ? 1 : 0;
+  }
+  const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
+  const int gh = up ? p->hin : p->hout, gw = up ? p->win : p->wout;
+  const bool pair = g_wide_pair && (((int64_t)p->batch * (gh / 16) * (gw / 8)) % 2 == 0);    // pairs = adjacent tiles along grid.x
+  if (up) return pair ? launch_wide_t<true, true>(p, wpk, s) : launch_wide_t<true, false>(p, wpk, s);
+  return pair ? launch_wide_t<false, true>(p, wpk, s) : launch_wide_t<false, false>(p, wpk, s);
 }
 
 }  // namespace e4s

@@ -250,7 +250,14 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     use_rj = use_tc and region_jobs is not None and labels is not None
 
     def launch():
-        if use_rj:
+        if use_rj and region_jobs.count is None:
+            # lazy region context: enqueue both candidates, the job count on the device runs exactly one of them
+            p.pred_count, p.pred_limit = region_jobs.count_dev.data_ptr(), region_jobs.limit
+            p.pred_run_if_gt = 0
+            L.conv_regions(p, pw.tc, region_jobs.jobs, region_jobs.count_dev, region_jobs.jobs.shape[0])
+            p.pred_run_if_gt = 1
+            L.conv(p, pw.tc)
+        elif use_rj:
             L.conv_regions(p, pw.tc, region_jobs.jobs, region_jobs.count_dev, region_jobs.count)
         else:
             L.conv(p, pw.tc if use_tc else None)
@@ -265,7 +272,7 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     ev0.record()
     launch()
     ev1.record()
-    PROFILE.append({"engine": "tc" if use_tc else "f32", "region_jobs": region_jobs.count if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
+    PROFILE.append({"engine": "tc" if use_tc else "f32", "region_jobs": (region_jobs.count if region_jobs.count is not None else -1) if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
                     "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1), "rgb": rgb is not None,
                     "bytes": 4.0 * (b * hin * win * pw.cin + (m_exec * pw.cout if out is not None else 0) + (3 * m_exec if rgb is not None else 0))})
     return out
@@ -308,8 +315,9 @@ class RegionJobs:
     """(16x8 tile, region present) job list of one masked layer resolution (e4s_region_tile_jobs)."""
     jobs: torch.Tensor
     count_dev: torch.Tensor
-    count: int
+    count: Optional[int]          # None: not read back (lazy context) -> the choice is made on the device (E4SConv.pred_*)
     tiles: int
+    limit: int = 0                # lazy: run the region-job kernel iff count <= limit, the per-row kernel otherwise
 
 
 class RegionCtx:
@@ -318,7 +326,10 @@ class RegionCtx:
     `job_keys` = [(hout, wout, up2)] of the masked 3x3 layers whose geometry the halo kernel takes: their
     per-tile region job lists are built here and the counts come back in the same (single) D2H read as the flag."""
 
-    def __init__(self, mask: torch.Tensor, job_keys=()):
+    def __init__(self, mask: torch.Tensor, job_keys=(), lazy: bool = False):
+        """lazy=True (Generator.forward): nothing is read back while the forward is being enqueued.  The mask is ASSUMED
+        one-hot (checked by `verify()` after the last launch; the caller re-runs on the generic path if not) and every
+        region-job decision is a device-side launch predicate."""
         if mask.dim() != 4:
             raise L.E4SError("mask must be [B,K,H,W]")
         self.mask = mask.contiguous().float()
@@ -327,23 +338,44 @@ class RegionCtx:
         meta = torch.zeros(1 + len(keys), device=self.mask.device, dtype=torch.int32)
         self.labels, _ = L.mask_labels(self.mask, meta[0:1])
         lists = [L.region_tile_jobs(self.labels, h, w, up, self.k, meta[1 + i:2 + i]) for i, (h, w, up) in enumerate(keys)]
-        host = meta.cpu()                               # one small D2H read per forward
-        self.onehot = int(host[0]) == 0
+        self.lazy = bool(lazy) and self.mask.is_cuda
+        if self.lazy:
+            self._host = torch.empty(meta.shape, dtype=torch.int32, pin_memory=True)
+            self._host.copy_(meta, non_blocking=True)
+            self._ev = torch.cuda.Event()
+            self._ev.record()
+            host = None
+            self.onehot = True                          # speculation; see verify()
+        else:
+            host = meta.cpu()                           # one small D2H read per forward
+            self.onehot = int(host[0]) == 0
         self.regions = self.k
         self.region_jobs = {}
         b = self.mask.shape[0]
         for i, (key, jl) in enumerate(zip(keys, lists)):
             h, w, up = key
             gh, gw = (h // 2, w // 2) if up else (h, w)
-            self.region_jobs[key] = RegionJobs(jl, meta[1 + i:2 + i], int(host[1 + i]), b * (gh // 16) * (gw // 8))
+            self.region_jobs[key] = RegionJobs(jl, meta[1 + i:2 + i], None if host is None else int(host[1 + i]),
+                                               b * (gh // 16) * (gw // 8))
+
+    def verify(self) -> bool:
+        """lazy contexts: was the one-hot assumption right?  (waits only for the tiny copy issued before the first layer)"""
+        if not self.lazy:
+            return True
+        self._ev.synchronize()
+        return int(self._host[0]) == 0
 
     def jobs_for(self, hout: int, wout: int, up2: bool, wide_ok: bool = False) -> Optional["RegionJobs"]:
         """The job list if this resolution has few enough regions per tile for the halo kernel to win
         (`wide_ok`: the layer can run on the 512-column gather kernel, which costs one pass whatever the mask)."""
         rj = self.region_jobs.get((hout, wout, bool(up2)))
-        if rj is None or not self.onehot or rj.count <= 0 or rj.count > REGION_JOB_RATIO * rj.tiles:
+        if rj is None or not self.onehot:
             return None
-        if wide_ok and rj.count > WIDE_OVER_REGION_JOBS * rj.tiles:
+        ratio = min(REGION_JOB_RATIO, WIDE_OVER_REGION_JOBS) if wide_ok else REGION_JOB_RATIO
+        if rj.count is None:                            # lazy: both kernels are enqueued, the device count picks one
+            rj.limit = int(ratio * rj.tiles)
+            return rj
+        if rj.count <= 0 or rj.count > ratio * rj.tiles:
             return None
         return rj
 

@@ -421,7 +421,7 @@ class Generator(nn.Module):
     @torch.no_grad()
     def forward(self, styles, structure_feats, mask, return_latents=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
-                use_structure_code=False):
+                use_structure_code=False, _ctx=None):
         if not input_is_latent:
             styles = [self.style(s) for s in styles]
         if noise is None:
@@ -437,7 +437,9 @@ class Generator(nn.Module):
         b, k, nl, sd = latent.shape
         if sd != self.style_dim or nl < self.n_latent:
             raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
-        ctx = E.RegionCtx(mask.to(latent.device), self._region_job_keys())
+        # lazy region context: no device->host read while the layers are being enqueued (the one-hot assumption is checked
+        # after the last launch; a soft / overlapping mask re-runs the forward on the generic per-region path)
+        ctx = _ctx if _ctx is not None else E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=True)
         if ctx.k != k or ctx.mask.shape[0] != b:
             raise L.E4SError("mask and latent disagree on batch / number of regions")
 
@@ -494,6 +496,12 @@ class Generator(nn.Module):
                 skip = rgb(to_rgb, out, skip)
             i += 2
         image = skip
+        if not ctx.verify():
+            # the mask was not one-hot: everything above used the label fast path -> redo with a synchronous context
+            # (which knows) on the generic float-mask path; `noise` / styles are already resolved, so the rerun sees the same inputs
+            sync_ctx = E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=False)
+            return self.forward([latent], structure_feats, mask, return_latents=return_latents, input_is_latent=True, noise=noise,
+                                randomize_noise=randomize_noise, use_structure_code=use_structure_code, _ctx=sync_ctx)
         if return_latents:
             return image, latent, intermediate_feats
         return image, None, intermediate_feats

@@ -101,6 +101,10 @@ typedef struct E4SConv {
    * rgb / rgb_skip are NCHW fp32 ([batch,3,hout,wout] / [batch,3,hout/2,wout/2]); rgb_fir is the 4x4 kernel of
    * Upsample (upfirdn2d up=2, pad=(2,1)).  With rgb set, out may be NULL: the activations are then never written. */
   float* rgb; const float* rgb_w; const float* rgb_smod; const float* rgb_bias; const float* rgb_skip; const float* rgb_fir;
+  /* Device-side launch predicate (NULL = always run): the kernel does its work only if (*pred_count > pred_limit) == (pred_run_if_gt != 0),
+   * otherwise every CTA exits at once.  Lets the host enqueue BOTH candidate kernels of a masked layer (per-(tile, region) jobs on the
+   * halo kernel vs. the per-row gather / wide kernel) without reading the job count back: no host synchronisation inside a forward. */
+  const int32_t* pred_count; int32_t pred_limit; int32_t pred_run_if_gt;
 } E4SConv;
 
 const char* e4s_last_error(void);

@@ -146,3 +146,17 @@ def test_bisenet_512_argmax_vs_oracle():
           f"largest oracle margin at a mismatch {worst:.3e}")
     assert d < 3e-5 * scale
     assert int(bad.sum()) <= 16 and worst < 2e-5 * scale
+
+
+def test_fused_torgb_matches_separate_torgb(monkeypatch):
+    """The ToRGB tail fused into the conv epilogue (256^2 layers of a 256^2 generator) against the stand-alone
+    torgb kernel reading the stored feature map: same modulated 1x1 conv, bias and FIR-upsampled skip."""
+    G, _ = _gen(256, 13, 5)
+    latent = synth.randn("fuse.latent", (2, 12, 18, 512), 21)
+    mask = synth.onehot(synth.blocky_labels(2, 12, 512, cells=32, seed=21), 12)
+    fused, _, _ = G([latent.cuda()], None, mask.cuda(), input_is_latent=True, randomize_noise=False)
+    monkeypatch.setenv("E4S_FUSE_RGB", "0")
+    plain, _, _ = G([latent.cuda()], None, mask.cuda(), input_is_latent=True, randomize_noise=False)
+    d = float((fused - plain).abs().max())
+    print(f"fused vs separate ToRGB: max|diff| {d:.3e} (range {float(plain.abs().max()):.2f})")
+    assert 0.0 < d < 2e-5 * max(float(plain.abs().max()), 1.0) or d == 0.0
