@@ -474,9 +474,9 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
   E4S_REQUIRE(!p->in_square, "conv_tc: in_square is only implemented by the fp32 engine");
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc: out must be 16-byte aligned with pitch %% 4 == 0");
   if (p->rgb)
-    E4S_REQUIRE(tc_halo_eligible(p) && p->mode != E4S_CONV_UP2_POLYPHASE && p->cout <= 256 && tc_epi_is_fast(*p) && p->regions == 1 &&
+    E4S_REQUIRE(tc_halo_eligible(p) && p->mode != E4S_CONV_UP2_POLYPHASE && p->cout <= 128 && tc_epi_is_fast(*p) && p->regions == 1 &&
                     (reinterpret_cast<uintptr_t>(p->rgb_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->rgb_smod) & 15) == 0,
-                "conv_tc: the fused ToRGB tail needs an un-masked same-resolution 3x3 layer of the halo kernel (cout <= 256, piecewise-linear activation)");
+                "conv_tc: the fused ToRGB tail needs an un-masked same-resolution 3x3 layer of the halo kernel (cout <= 128: one n-tile per pixel, piecewise-linear activation)");
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
   if (p->smod) E4S_REQUIRE((reinterpret_cast<uintptr_t>(p->smod) & 15) == 0, "conv_tc: smod must be 16-byte aligned");
   if (p->res) E4S_REQUIRE(p->res_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->res) & 15) == 0, "conv_tc: res must be 16-byte aligned with pitch %% 4 == 0");

@@ -64,7 +64,8 @@ def halo_geometry_ok(cin: int, cout: int, hin: int, win: int, up2: bool, kh: int
 
 def rgb_fusable(cin: int, cout: int, h: int, w: int) -> bool:
     """Can a same-resolution 3x3 layer carry the fused ToRGB tail (e4s_b200.h, struct E4SConv rgb*)?"""
-    return _ENGINE == "tc" and tc_available() and cout <= 256 and halo_geometry_ok(cin, cout, h, w, False) and \
+    # cout <= 128: the halo kernel runs wider layers as 128-column n-tiles, and the tail needs a pixel's whole channel row in one job
+    return _ENGINE == "tc" and tc_available() and cout <= 128 and halo_geometry_ok(cin, cout, h, w, False) and \
         os.environ.get("E4S_FUSE_RGB", "1") != "0"
 
 

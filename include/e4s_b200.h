@@ -96,7 +96,7 @@ typedef struct E4SConv {
   int32_t act; float act_slope, act_gain; const float* act_prelu;
   float* out; int64_t out_pitch; int32_t accumulate;
   /* Fused ToRGB tail (reference models/stylegan2/model.py:439-479 applied to this layer's activated output without
-   * re-reading it; e4s_conv_tc only, un-masked same-resolution 3x3 layers with cout <= 256):
+   * re-reading it; e4s_conv_tc only, un-masked same-resolution 3x3 layers with cout <= 128):
    *   rgb[b,c,y,x] = sum_co act_out[b,y,x,co] * rgb_w[c,co] * rgb_smod[b,co] + rgb_bias[c] + FIR-upsample(rgb_skip)[b,c,y,x]
    * rgb / rgb_skip are NCHW fp32 ([batch,3,hout,wout] / [batch,3,hout/2,wout/2]); rgb_fir is the 4x4 kernel of
    * Upsample (upfirdn2d up=2, pad=(2,1)).  With rgb set, out may be NULL: the activations are then never written. */
