@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       int sy = nearest_src(rw.oy, p.lab_h, p.hout), sx = nearest_src(rw.ox, p.lab_w, p.wout);
       pw = __ldg(p.pixw + (int64_t)rw.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
     }
+    const float corr = tc_acc_unbias(num_kc * (TC_BK / 16) * 3);      // 3 accumulating MMAs per K step of 16
     TcEpiRow er;
     er.pix = pix;
     er.drow = drow;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
             const float4 sc = ldg4(p.ch_scale + n);
             mul[qd].x *= sc.x; mul[qd].y *= sc.y; mul[qd].z *= sc.z; mul[qd].w *= sc.w;
           }
+          mul[qd].x *= corr; mul[qd].y *= corr; mul[qd].z *= corr; mul[qd].w *= corr;
           add[qd] = p.ch_shift ? ldg4(p.ch_shift + n) : make_float4(0.f, 0.f, 0.f, 0.f);
           sl[qd] = make_float4(tc_epi_slope(p, n), tc_epi_slope(p, n + 1), tc_epi_slope(p, n + 2), tc_epi_slope(p, n + 3));
         }
@@ -310,6 +312,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
         float acc[16];
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] *= corr;
         if (live) tc_epilogue16(p, acc, n_base + c0, er);
       }
     }

@@ -327,6 +327,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     const bool noise1 = p.noise && p.noise_sc == 0;
     const bool fast = tc_epi_is_fast(p) && !(dbg & (1 | 2 | 8 | 16 | 128));    // bit7: force the generic epilogue
     const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
+    // accumulate steps into the main accumulator: 9 taps x ksteps per group, 3 MMAs each (2 where hi|lo weights merge along N)
+    const float corr = tc_acc_unbias(G * 9 * ksteps * (NC ? 2 : 3));
     // fused ToRGB tail (host guarantees: !UP, one n-tile, no region jobs, fast epilogue)
     const bool do_rgb = !UP && p.rgb != nullptr;
     const int sk_h = p.hout >> 1, sk_w = p.wout >> 1;
@@ -388,7 +390,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           const int ng = jb.nt * BN + n;
           float mul = drow ? __ldg(drow + ng) : 1.f;
           if (p.ch_scale) mul *= __ldg(p.ch_scale + ng);
-          svw[n] = mul;
+          svw[n] = mul * (fast ? corr : 1.f);            // the generic path scales the accumulator itself
           svw[BN + n] = p.ch_shift ? __ldg(p.ch_shift + ng) : 0.f;
           svw[2 * BN + n] = tc_epi_slope(p, ng);
           if (do_rgb) {
@@ -490,6 +492,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
 #pragma unroll
               for (int j = 0; j < 16; ++j) acc[j] += acc2[j];
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] *= corr;
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.f;

@@ -373,6 +373,14 @@ __device__ __forceinline__ void tc_epilogue16_sv(const E4SConv& p, const float (
   }
 }
 
+// The tensor core's fp32 accumulate truncates: every tcgen05.mma into the same TMEM accumulator shrinks the running sum by
+// ~2^-26 relative on average (measured, tests/micro/acc_bias.py: least-squares scale of the result against fp64 is
+// -1.5e-8 x accumulate steps for K = 576 ... 4608, while the CUDA-core fp32 engine shows none).  A K = 4608 layer loses
+// 1.3e-5, and because the synthesis network is positively homogeneous the per-layer losses ADD UP along the 17 layers
+// into the dominant, coherent part of the end-to-end error.  The epilogues multiply the accumulator by this factor to
+// remove the mean of that bias (the random part of the truncation stays).
+__host__ __device__ __forceinline__ float tc_acc_unbias(int mma_steps) { return 1.f + 1.5e-8f * (float)mma_steps; }
+
 // Fast epilogue (chosen once per kernel, outside every loop): no residual / float mask / accumulate / per-channel noise and an
 // activation of the piecewise-linear family.  sv = [mul | add | negative-side slope] per channel; NONE, ReLU, leaky ReLU
 // and PReLU all are  t = acc*mul + (add + nz);  out = (t < 0 ? t*slope : t) * gain  -- no branches, no constant-bank
