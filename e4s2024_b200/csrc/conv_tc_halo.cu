@@ -342,6 +342,9 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
 #pragma unroll
         for (int d = 0; d < 2; ++d) fk[2 * a + d] = __ldg(p.rgb_fir + (3 - (ky0 + 2 * a)) * 4 + (3 - (kx0 + 2 * d)));
     }
+    // per-thread constants of the skip taps: y0 / x0 are multiples of 16 / 8, so (oy0 - 2 + ky0) >> 1 = y0/2 + sk_dy
+    const int sk_dy = (ty - 2 + ky0) >> 1, sk_dx = (tx - 2 + kx0) >> 1;
+    const int sk_plane = sk_h * sk_w;
     const float rb0 = (do_rgb && p.rgb_bias) ? __ldg(p.rgb_bias) : 0.f, rb1 = (do_rgb && p.rgb_bias) ? __ldg(p.rgb_bias + 1) : 0.f,
                 rb2 = (do_rgb && p.rgb_bias) ? __ldg(p.rgb_bias + 2) : 0.f;
 
@@ -405,18 +408,15 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       // skip taps of this pixel: issued before the accumulator wait, consumed (first arithmetic) after the channel loop
       float skv[12];
       if (do_rgb && p.rgb_skip) {
-        const int sy0 = (oy0 - 2 + ky0) >> 1, sx0 = (ox0 - 2 + kx0) >> 1;     // arithmetic shift: -1 at the top / left border
+        const int sy0 = (jb.y0 >> 1) + sk_dy, sx0 = (jb.x0 >> 1) + sk_dx;     // -1 at the top / left border
+        const bool vy[2] = {sy0 >= 0, sy0 + 1 < sk_h}, vx[2] = {sx0 >= 0, sx0 + 1 < sk_w};
+        const float* sp = p.rgb_skip + (int64_t)jb.b * 3 * sk_plane + (sy0 * sk_w + sx0);   // 32-bit offsets from here on
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float* sp = p.rgb_skip + ((int64_t)jb.b * 3 + c) * sk_h * sk_w;
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
           for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              const int sy = sy0 + a, sx = sx0 + d;
-              skv[c * 4 + 2 * a + d] = (sy >= 0 && sy < sk_h && sx >= 0 && sx < sk_w) ? __ldg(sp + (int64_t)sy * sk_w + sx) : 0.f;
-            }
-        }
+            for (int d = 0; d < 2; ++d) skv[c * 4 + 2 * a + d] = (vy[a] && vx[d]) ? __ldg(sp + (c * sk_plane + a * sk_w + d)) : 0.f;
       }
       HL_LAP(1, 3);
       mbar_wait(bar_afull + 8 * set, use & 1);
