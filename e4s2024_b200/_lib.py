@@ -53,7 +53,7 @@ EXPORTS = [
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
-    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32",
+    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32",
 ]
 
 _lib = None
@@ -218,6 +218,15 @@ def labels_to_onehot(labels: torch.Tensor, k: int) -> torch.Tensor:
     b, h, w = labels.shape
     out = torch.empty(b, k, h, w, device=labels.device, dtype=torch.float32)
     _check(lib().e4s_labels_to_onehot_f32(_fp(labels.data_ptr()), b, k, h, w, _fp(out.data_ptr()), _stream()), "e4s_labels_to_onehot_f32")
+    return out
+
+
+def swap_comp_styles(target: torch.Tensor, source: torch.Tensor, comp_mask: int, below_face: bool) -> torch.Tensor:
+    _req(target), _req(source)
+    b, k, d = target.shape
+    out = torch.empty_like(target)
+    _check(lib().e4s_swap_comp_styles_f32(_fp(target.data_ptr()), _fp(source.data_ptr()), _fp(out.data_ptr()), b, k, d,
+                                          C.c_uint32(comp_mask), int(below_face), _stream()), "e4s_swap_comp_styles_f32")
     return out
 
 

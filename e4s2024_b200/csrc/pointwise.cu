@@ -447,3 +447,46 @@ extern "C" int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, 
   }
   return check_launch("torgb");
 }
+
+// ---- style recombination between encoder and generator (reference swap_face_fine/swap_face_mask.py:336-367) --------------
+// One CTA per (sample, component).  out = target's vector, replaced by the source's where the component is swapped; ears (7)
+// are always the average, ear-rings (11) always the target's, below-face (8) the average when asked, and the mouth (9) falls
+// back to the target's when the source has no mouth pixels (its masked mean is the zero vector).
+namespace e4s {
+__global__ void __launch_bounds__(128) swap_comp_styles_kernel(const float* __restrict__ t, const float* __restrict__ s, float* __restrict__ out,
+                                                               int ncomp, int dim, uint32_t comp_mask, int below_face) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* tv = t + ((int64_t)b * ncomp + c) * dim;
+  const float* sv = s + ((int64_t)b * ncomp + c) * dim;
+  float* ov = out + ((int64_t)b * ncomp + c) * dim;
+  int mode = (comp_mask >> c) & 1u;                    // 0 target, 1 source, 2 average
+  if (c == 7) mode = 2;
+  if (c == 11) mode = 0;
+  if (c == 8 && below_face) mode = 2;
+  if (c == 9) {                                        // torch.sum(style_vectors2[:, 9, :]) == 0, per sample
+    __shared__ float red[4];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < dim; i += 128) acc += sv[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (red[0] + red[1] + red[2] + red[3] == 0.f) mode = 0;
+  }
+  for (int i = threadIdx.x; i < dim; i += 128) {
+    const float a = tv[i], bb = sv[i];
+    ov[i] = mode == 0 ? a : (mode == 1 ? bb : (a + bb) / 2.f);
+  }
+}
+}  // namespace e4s
+
+extern "C" int e4s_swap_comp_styles_f32(const float* target, const float* source, float* out, int batch, int ncomp, int dim,
+                                        uint32_t comp_mask, int below_face, void* stream) {
+  using namespace e4s;
+  E4S_REQUIRE(target && source && out && batch > 0 && dim > 0, "swap_comp_styles: bad args");
+  E4S_REQUIRE(ncomp >= 12 && ncomp <= 32, "swap_comp_styles: the recombination rules address components 7, 8, 9, 11 (ncomp=%d)", ncomp);
+  swap_comp_styles_kernel<<<dim3((unsigned)ncomp, (unsigned)batch), 128, 0, as_stream(stream)>>>(target, source, out, ncomp, dim, comp_mask,
+                                                                                              below_face);
+  return check_launch("swap_comp_styles");
+}
+

@@ -216,6 +216,13 @@ int e4s_bicubic_down_norm_f32(const float* x, int batch, int hin, int win, int f
 /* labels u8 [batch,h,w] -> one-hot float [batch,k,h,w] (labelMap2OneHot, utils/torch_utils.py:207-213) */
 int e4s_labels_to_onehot_f32(const uint8_t* labels, int batch, int k, int h, int w, float* onehot, void* stream);
 
+/* Style recombination between encoder and generator (swap_comp_style_vector, reference swap_face_fine/swap_face_mask.py:336-367):
+ * target/source/out [batch, ncomp, dim] fp32; bit c of comp_mask = component c takes the source's vector.  Components 7 (ears:
+ * average), 11 (ear-rings: target), 8 (below-face: average when below_face) and 9 (mouth: target when the source's vector sums to
+ * exactly 0, evaluated per sample) follow the reference's fixed rules. */
+int e4s_swap_comp_styles_f32(const float* target, const float* source, float* out, int batch, int ncomp, int dim,
+                             uint32_t comp_mask, int below_face, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

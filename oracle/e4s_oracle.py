@@ -435,3 +435,18 @@ def label_to_onehot(label: torch.Tensor, num_cls: int) -> torch.Tensor:
     """utils/torch_utils.py:207-213 (labelMap2OneHot): [B,1,H,W] int64 -> [B,num_cls,H,W] float."""
     b, _, h, w = label.shape
     return torch.zeros(b, num_cls, h, w).scatter_(1, label, 1.0)
+
+
+def swap_comp_style_vector(sv1: torch.Tensor, sv2: torch.Tensor, comp_indices, below_face_interpolation: bool = False) -> torch.Tensor:
+    """swap_face_fine/swap_face_mask.py:336-367 restated per sample (the reference is batch 1: its
+    `torch.sum(style_vectors2[:, 9, :]) == 0` test then coincides with the per-sample test used here)."""
+    out = sv1.clone()
+    for c in comp_indices:                                   # :347-348
+        out[:, c, :] = sv2[:, c, :]
+    out[:, 7, :] = (sv1[:, 7, :] + sv2[:, 7, :]) / 2         # :354 ears: always the average
+    out[:, 11, :] = sv1[:, 11, :]                            # :357 ear-rings: always the target's
+    if below_face_interpolation:                             # :360-361
+        out[:, 8, :] = (sv1[:, 8, :] + sv2[:, 8, :]) / 2
+    empty = sv2[:, 9, :].sum(dim=1) == 0                     # :364-365 source without a mouth region -> target's vector
+    out[empty, 9, :] = sv1[empty, 9, :]
+    return out

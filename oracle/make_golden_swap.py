@@ -1,0 +1,30 @@
+"""Golden vectors for swap_comp_style_vector from the REFERENCE's own function (swap_face_fine/swap_face_mask.py:336-367),
+executed in the build container:  python oracle/make_golden_swap.py   -> tests/golden/swap_comp_style_vector.npz
+TEST INFRASTRUCTURE ONLY."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from e4s2024_b200 import synth  # noqa: E402
+from oracle import e4s_oracle as orc  # noqa: E402
+from swap_face_fine.swap_face_mask import swap_comp_style_vector as ref_fn  # noqa: E402
+
+CASES = [([1, 2, 3, 5, 6, 9], False, False), ([1, 2, 3, 5, 6, 9], True, False), ([4, 8, 9, 10], False, True), ([], False, True)]
+arrs, worst = {}, 0.0
+for i, (comps, below, empty_mouth) in enumerate(CASES):
+    a = synth.randn(f"swapsv.t{i}", (1, 12, 512), 40 + i)
+    b = synth.randn(f"swapsv.s{i}", (1, 12, 512), 50 + i)
+    if empty_mouth:
+        b[:, 9, :] = 0
+    y = ref_fn(a, b, comps, belowFace_interpolation=below)
+    worst = max(worst, float((y - orc.swap_comp_style_vector(a, b, comps, below)).abs().max()))
+    arrs[f"t{i}"], arrs[f"s{i}"], arrs[f"y{i}"] = a.numpy(), b.numpy(), y.numpy()
+    arrs[f"cfg{i}"] = np.array([int(below)] + list(comps), dtype=np.int64)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "swap_comp_style_vector.npz"), n=np.array(len(CASES)), **arrs)
+print("oracle vs reference: max|diff|", worst)

@@ -189,6 +189,27 @@ def labels_to_onehot(labels, k):
     return F.one_hot(labels.long(), k).permute(0, 3, 1, 2).float().contiguous()
 
 
+def swap_comp_styles(target, source, comp_mask, below_face):
+    """e4s_swap_comp_styles_f32 restated with torch (mode per component: target / source / average)."""
+    out = target.clone()
+    k = target.shape[1]
+    for c in range(k):
+        mode = (comp_mask >> c) & 1
+        if c == 7:
+            mode = 2
+        if c == 11:
+            mode = 0
+        if c == 8 and below_face:
+            mode = 2
+        if mode == 1:
+            out[:, c] = source[:, c]
+        elif mode == 2:
+            out[:, c] = (target[:, c] + source[:, c]) / 2
+    empty = source[:, 9].sum(dim=1) == 0
+    out[empty, 9] = target[empty, 9]
+    return out
+
+
 def torgb(x_nhwc, cin, smod, wrgb, labels, regions, lab_hw, pixw, pixw_sb, bias, skip, fir, rgb, accumulate):
     b, h, w, _ = x_nhwc.shape
     yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
@@ -300,7 +321,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
 
 
 _NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "bias_act", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
-          "mask_labels", "labels_to_onehot", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
+          "mask_labels", "labels_to_onehot", "swap_comp_styles", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
 

@@ -115,3 +115,12 @@ def test_seg_lut(golden):
     lab = torch.tensor([[[[0, 2], [1, 1]]]])
     oh = orc.label_to_onehot(lab, 3)
     assert oh.shape == (1, 3, 2, 2) and oh.sum() == 4 and oh[0, 2, 0, 1] == 1
+
+
+def test_swap_comp_style_vector(golden):
+    g = golden("swap_comp_style_vector")
+    for i in range(int(g["n"])):
+        cfg = g[f"cfg{i}"]
+        y = orc.swap_comp_style_vector(T(g[f"t{i}"]), T(g[f"s{i}"]), [int(c) for c in cfg[1:]], bool(cfg[0]))
+        close(y, g[f"y{i}"], 0.0)
+

@@ -193,3 +193,24 @@ def test_face_parser(golden, dev):
         bad = got != want
         tie = 2e-5 * float(p["logit_absmax"])          # fp32 reassociation noise at the synthetic logit scale
         assert bad.sum() == 0 or (bad.sum() <= 8 and float(p["margin"][bad].max()) < tie), int(bad.sum())
+
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_swap_comp_style_vector(golden, dev):
+    """the recombination step between encoder and generator, bit-exact vs the reference's function,
+    plus a batch whose samples differ in whether the source has a mouth region (per-sample rule, no host read-back)."""
+    from e4s2024_b200.swap_face_mask import swap_comp_style_vector
+    g = golden("swap_comp_style_vector")
+    with ctx_for(dev):
+        ts, ss = [], []
+        for i in range(int(g["n"])):
+            cfg = g[f"cfg{i}"]
+            t, s_ = to(dev, T(g[f"t{i}"]), T(g[f"s{i}"]))
+            y = swap_comp_style_vector(t, s_, [int(c) for c in cfg[1:]], belowFace_interpolation=bool(cfg[0]))
+            assert maxdiff(y, g[f"y{i}"]) == 0.0
+            ts.append(T(g[f"t{i}"]))
+            ss.append(T(g[f"s{i}"]))
+        tb, sb = to(dev, torch.cat(ts), torch.cat(ss))
+        yb = swap_comp_style_vector(tb, sb, [1, 2, 9], belowFace_interpolation=True)
+        assert maxdiff(yb, orc.swap_comp_style_vector(torch.cat(ts), torch.cat(ss), [1, 2, 9], True)) == 0.0
+
