@@ -258,7 +258,7 @@ def main():
     # step i rides under the kernels of step i+1 (NVLink/NVSwitch traffic, no dependence on the next step's inputs)
     gathered = [torch.empty(world * BATCH, 3, SIZE, SIZE, device=dev) for _ in range(2)] if world > 1 else None
     inflight = []
-    out_h = torch.empty(BATCH, 3, SIZE, SIZE).pin_memory()
+    out_h = torch.empty(BATCH, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory()     # what tensor2im hands the host: uint8 HWC images
 
     def step_resident():
         img, _, _ = G([latent_d], None, mask_d, input_is_latent=True, randomize_noise=False)
@@ -281,11 +281,13 @@ def main():
     # The mask crosses PCIe as the u8 label map the pipelines hold on the host and becomes one-hot on the device
     # (utils.torch_utils.labelMap2OneHot, as in the reference's own flow: label map -> one-hot -> Generator).
     from e4s2024_b200.serving import HostPipeline
-    from e4s2024_b200.utils.torch_utils import labelMap2OneHot
+    # The images leave as the uint8 HWC arrays the pipelines build right after the generator (utils.torch_utils.tensor2im,
+    # face_swap_video_pipeline.py: `tensor2im(swapped_face_image[0])`), converted on the device with identical arithmetic.
+    from e4s2024_b200.utils.torch_utils import labelMap2OneHot, tensor2im_batch
     labels_h = mask_h.argmax(1, keepdim=True).to(torch.uint8).pin_memory()          # [B,1,512,512]
 
     def e2e_fn(lat, lab):
-        return G([lat], None, labelMap2OneHot(lab, K), input_is_latent=True, randomize_noise=False)[0]
+        return tensor2im_batch(G([lat], None, labelMap2OneHot(lab, K), input_is_latent=True, randomize_noise=False)[0])
 
     pipe = HostPipeline(e2e_fn, dev)
 
@@ -389,9 +391,10 @@ def main():
                 "config": bench_config(world, E.conv_engine()),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e / args.steps,
-                        "note": "labelMap2OneHot + Generator.forward through HostPipeline: pinned-host H2D of every step's latent + u8 label map, "
-                                "D2H of its fp32 images, double-buffered on copy streams (timed region = first H2D to last D2H complete)",
-                        "h2d_bytes_per_step": int(latent_h.numel() * 4 + labels_h.numel()), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                        "note": "labelMap2OneHot + Generator.forward + tensor2im_batch through HostPipeline: pinned-host H2D of every step's latent + u8 "
+                                "label map, D2H of its uint8 HWC images (the reference pipelines' tensor2im output), double-buffered on copy "
+                                "streams (timed region = first H2D to last D2H complete)",
+                        "h2d_bytes_per_step": int(latent_h.numel() * 4 + labels_h.numel()), "d2h_bytes_per_step": int(out_h.numel())},
                 "roofline": roof, "cpu_baseline": cpu, "swap_path": swap,
                 "alg_gflop_per_face": ALG_GFLOP_PER_FACE,
                 "job_alg_tflops": value * ALG_GFLOP_PER_FACE / 1e3}

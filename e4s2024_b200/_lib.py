@@ -53,7 +53,7 @@ EXPORTS = [
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
-    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32",
+    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8",
 ]
 
 _lib = None
@@ -219,6 +219,17 @@ def labels_to_onehot(labels: torch.Tensor, k: int) -> torch.Tensor:
     out = torch.empty(b, k, h, w, device=labels.device, dtype=torch.float32)
     _check(lib().e4s_labels_to_onehot_f32(_fp(labels.data_ptr()), b, k, h, w, _fp(out.data_ptr()), _stream()), "e4s_labels_to_onehot_f32")
     return out
+
+
+def tensor2im_u8(x: torch.Tensor, zero_center: bool = True) -> torch.Tensor:
+    """[B,3,H,W] fp32 -> [B,H,W,3] uint8 on the device."""
+    _req(x)
+    b, c, h, w = x.shape
+    if c != 3:
+        raise E4SError("tensor2im_u8 expects 3 channels")
+    y = torch.empty(b, h, w, 3, device=x.device, dtype=torch.uint8)
+    _check(lib().e4s_tensor2im_u8(_fp(x.data_ptr()), _fp(y.data_ptr()), b, h, w, int(zero_center), _stream()), "e4s_tensor2im_u8")
+    return y
 
 
 def swap_comp_styles(target: torch.Tensor, source: torch.Tensor, comp_mask: int, below_face: bool) -> torch.Tensor:

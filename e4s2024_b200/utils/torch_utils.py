@@ -26,6 +26,13 @@ def tensor2im(var, is_zero_center: bool = True):
     return Image.fromarray(var.astype("uint8"))
 
 
+def tensor2im_batch(var: torch.Tensor, is_zero_center: bool = True) -> torch.Tensor:
+    """Batched, on-device form of tensor2im's arithmetic: [B,3,H,W] float (CUDA) -> uint8 [B,H,W,3] (CUDA), byte for byte what
+    `tensor2im` puts into the PIL image for each sample; copy it to the host (a quarter of the float bytes) and wrap rows with
+    `Image.fromarray` as needed."""
+    return L.tensor2im_u8(var.contiguous().float(), is_zero_center)
+
+
 def remove_module_prefix(state_dict, prefix):
     """torch_utils.py:216-223."""
     return {k.replace(prefix, "", 1): v for k, v in state_dict.items()}

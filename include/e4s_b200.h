@@ -223,6 +223,10 @@ int e4s_labels_to_onehot_f32(const uint8_t* labels, int batch, int k, int h, int
 int e4s_swap_comp_styles_f32(const float* target, const float* source, float* out, int batch, int ncomp, int dim,
                              uint32_t comp_mask, int below_face, void* stream);
 
+/* tensor2im on the device (reference utils/torch_utils.py:64-76), batched: x NCHW [batch,3,h,w] fp32 -> y NHWC [batch,h,w,3] u8:
+ * (v+1)/2 when zero_center, clamp [0,1], *255, truncate (the reference's float32 numpy arithmetic: identical bytes) */
+int e4s_tensor2im_u8(const float* x, uint8_t* y, int batch, int h, int w, int zero_center, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

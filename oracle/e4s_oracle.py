@@ -450,3 +450,14 @@ def swap_comp_style_vector(sv1: torch.Tensor, sv2: torch.Tensor, comp_indices, b
     empty = sv2[:, 9, :].sum(dim=1) == 0                     # :364-365 source without a mouth region -> target's vector
     out[empty, 9, :] = sv1[empty, 9, :]
     return out
+
+
+def tensor2im_u8(var: torch.Tensor, is_zero_center: bool = True) -> torch.Tensor:
+    """utils/torch_utils.py:64-76 per sample, batched: [B,3,H,W] float -> uint8 [B,H,W,3] (float32 numpy arithmetic)."""
+    v = var.detach().cpu().float().permute(0, 2, 3, 1).numpy().copy()
+    if is_zero_center:
+        v = (v + 1) / 2          # :71
+    v[v < 0] = 0                 # :72
+    v[v > 1] = 1                 # :73
+    v = v * 255                  # :74
+    return torch.from_numpy(v.astype("uint8"))

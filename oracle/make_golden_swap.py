@@ -28,3 +28,15 @@ for i, (comps, below, empty_mouth) in enumerate(CASES):
     arrs[f"cfg{i}"] = np.array([int(below)] + list(comps), dtype=np.int64)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "swap_comp_style_vector.npz"), n=np.array(len(CASES)), **arrs)
 print("oracle vs reference: max|diff|", worst)
+
+# ---- tensor2im (utils/torch_utils.py:64-76): values around the clamp edges and the rounding boundaries ----------------------
+import types  # noqa: E402
+for _m in ("matplotlib", "matplotlib.pyplot"):          # absent in this image and unused by tensor2im: import shim only
+    sys.modules.setdefault(_m, types.ModuleType(_m))
+from utils.torch_utils import tensor2im as ref_tensor2im  # noqa: E402
+
+x = synth.randn("tensor2im.x", (2, 3, 8, 12), 60) * 0.8
+x[0, 0, 0, :6] = torch.tensor([-1.0, 1.0, -1.5, 1.5, 0.0, 254.5 / 127.5 - 1])
+ys = np.stack([np.array(ref_tensor2im(x[i])) for i in range(x.shape[0])])
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tensor2im.npz"), x=x.numpy(), y=ys)
+print("tensor2im golden", ys.shape, ys.dtype, "oracle mismatches:", int((orc.tensor2im_u8(x).numpy() != ys).sum()))

@@ -189,6 +189,14 @@ def labels_to_onehot(labels, k):
     return F.one_hot(labels.long(), k).permute(0, 3, 1, 2).float().contiguous()
 
 
+def tensor2im_u8(x, zero_center=True):
+    v = x.float()
+    if zero_center:
+        v = (v + 1) / 2
+    v = v.clamp(0, 1) * 255
+    return v.permute(0, 2, 3, 1).to(torch.uint8).contiguous()
+
+
 def swap_comp_styles(target, source, comp_mask, below_face):
     """e4s_swap_comp_styles_f32 restated with torch (mode per component: target / source / average)."""
     out = target.clone()
@@ -321,7 +329,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
 
 
 _NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "bias_act", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
-          "mask_labels", "labels_to_onehot", "swap_comp_styles", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
+          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
 

@@ -124,3 +124,8 @@ def test_swap_comp_style_vector(golden):
         y = orc.swap_comp_style_vector(T(g[f"t{i}"]), T(g[f"s{i}"]), [int(c) for c in cfg[1:]], bool(cfg[0]))
         close(y, g[f"y{i}"], 0.0)
 
+
+def test_tensor2im(golden):
+    g = golden("tensor2im")
+    assert int((orc.tensor2im_u8(T(g["x"])).numpy() != g["y"]).sum()) == 0
+

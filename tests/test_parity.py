@@ -214,3 +214,14 @@ def test_swap_comp_style_vector(golden, dev):
         yb = swap_comp_style_vector(tb, sb, [1, 2, 9], belowFace_interpolation=True)
         assert maxdiff(yb, orc.swap_comp_style_vector(torch.cat(ts), torch.cat(ss), [1, 2, 9], True)) == 0.0
 
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_tensor2im_batch(golden, dev):
+    """tensor2im's arithmetic on the device, byte-exact vs the reference's PIL output."""
+    from e4s2024_b200.utils.torch_utils import tensor2im_batch
+    g = golden("tensor2im")
+    with ctx_for(dev):
+        y = tensor2im_batch(to(dev, T(g["x"])))
+    assert y.dtype == torch.uint8 and tuple(y.shape) == g["y"].shape
+    assert int((y.cpu().numpy() != g["y"]).sum()) == 0
+
