@@ -381,7 +381,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_swap_path:
         del G, pipe
         torch.cuda.empty_cache()
-        swap = swap_path_line(dev)
+        try:
+            swap = swap_path_line(dev)
+        except Exception as e:                          # the secondary line must never take the headline down with it
+            swap = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline()
         line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -210,9 +210,9 @@ __global__ void labels_to_onehot_kernel(const uint8_t* __restrict__ labels, int 
 // adds bias and the 2x2 non-zero taps of the zero-insert-upsampled skip (closed form of upfirdn2d(up=2, pad=(2,1)))
 // and writes the three NCHW planes fully coalesced.
 // ------------------------------------------------------------------------------------------------
-constexpr int TORGB_TILE = 256;
+constexpr int TORGB_TILE_MAX = 256;
 
-template <int LP>
+template <int LP, int TORGB_TILE>
 __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, int64_t x_pitch, int64_t npix, int h, int w,
                                                     int cin, const float* __restrict__ smod, const float* __restrict__ wrgb,
                                                     const uint8_t* __restrict__ labels, int regions, int lab_h, int lab_w,
@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
   // ---- phase A: dot products ---------------------------------------------------------------------
   // TU pixels per warp step with independent accumulators: every step is a chain of dependent global loads (label ->
   // style row -> features), and one pixel per step made the kernel pure latency (90 us per launch whatever the grid size).
-  constexpr int TU = 4;
+  constexpr int TU = 2;
+  constexpr int NCI = 4;               // channel steps issued together: all their loads are in flight before the first FMA
   for (int t0 = warp * PPW + sub; t0 < TORGB_TILE; t0 += 8 * PPW * TU) {       // whole warp iterates together (t differs by sub only)
     float a0[TU], a1[TU], a2[TU];
     const float* xr[TU];
@@ -254,23 +255,32 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
         sr[u] = smod + ((int64_t)b * regions + r) * cin;
       }
     }
-    for (int ci = ll * 4; ci < cin; ci += LP * 4) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrgb + ci));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci));
-      const float4 w2 = __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci));
-      float4 v[TU], sm[TU];
+    for (int ci0 = ll * 4; ci0 < cin; ci0 += LP * 4 * NCI) {
+      float4 w0[NCI], w1[NCI], w2[NCI], v[TU][NCI], sm[TU][NCI];
 #pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        v[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(xr[u] + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        sm[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(sr[u] + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < NCI; ++k) {
+        const int ci = ci0 + k * LP * 4;
+        const bool in = ci < cin;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        w0[k] = in ? __ldg(reinterpret_cast<const float4*>(wrgb + ci)) : z;
+        w1[k] = in ? __ldg(reinterpret_cast<const float4*>(wrgb + cin + ci)) : z;
+        w2[k] = in ? __ldg(reinterpret_cast<const float4*>(wrgb + 2 * cin + ci)) : z;
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+          v[u][k] = (in && ok[u]) ? __ldg(reinterpret_cast<const float4*>(xr[u] + ci)) : z;
+          sm[u][k] = (in && ok[u]) ? __ldg(reinterpret_cast<const float4*>(sr[u] + ci)) : z;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        v[u].x *= sm[u].x; v[u].y *= sm[u].y; v[u].z *= sm[u].z; v[u].w *= sm[u].w;
-        a0[u] += v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
-        a1[u] += v[u].x * w1.x + v[u].y * w1.y + v[u].z * w1.z + v[u].w * w1.w;
-        a2[u] += v[u].x * w2.x + v[u].y * w2.y + v[u].z * w2.z + v[u].w * w2.w;
-      }
+      for (int k = 0; k < NCI; ++k)          // same order of additions per pixel as one channel step at a time
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+          float4 q = v[u][k];
+          q.x *= sm[u][k].x; q.y *= sm[u][k].y; q.z *= sm[u][k].z; q.w *= sm[u][k].w;
+          a0[u] += q.x * w0[k].x + q.y * w0[k].y + q.z * w0[k].z + q.w * w0[k].w;
+          a1[u] += q.x * w1[k].x + q.y * w1[k].y + q.z * w1[k].z + q.w * w1[k].w;
+          a2[u] += q.x * w2[k].x + q.y * w2[k].y + q.z * w2[k].z + q.w * w2[k].w;
+        }
     }
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
   // ---- phase B: bias + skip + coalesced NCHW store -------------------------------------------------
   const int t = threadIdx.x;
   const int64_t pix = tile0 + t;
-  if (pix >= npix) return;
+  if (t >= TORGB_TILE || pix >= npix) return;
   const int b = (int)(pix / hw);
   const int rem = (int)(pix - (int64_t)b * hw);
   const int y = rem / w, xx = rem - y * w;
@@ -434,17 +444,27 @@ extern "C" int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, 
   E4S_REQUIRE(regions > 0 && (!(labels || pixw) || (lab_h > 0 && lab_w > 0)), "torgb: bad region args");
   int64_t npix = (int64_t)batch * h * w;
   cudaStream_t s = as_stream(stream);
-  const unsigned tiles = (unsigned)ceil_div64(npix, TORGB_TILE);
+  // small images (the 4^2 .. 64^2 layers): 32-pixel tiles, so a CTA's 8 warps share 32 pixels instead of walking 256 one after
+  // the other (the kernel is a chain of dependent L2 round trips per pixel step: 75-90 us per launch whatever the size before)
+  const bool small = npix <= 32 * 148 * 16;
+  const unsigned tiles = (unsigned)ceil_div64(npix, small ? 32 : 256);
+#define E4S_TORGB_LAUNCH(LPV)                                                                                                        \
+  do {                                                                                                                             \
+    if (small)                                                                                                                     \
+      torgb_kernel<LPV, 32><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w, pixw, pixw_sb, \
+                                                  bias, skip, fir, rgb, accumulate);                                                \
+    else                                                                                                                           \
+      torgb_kernel<LPV, 256><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w, pixw, pixw_sb, \
+                                                   bias, skip, fir, rgb, accumulate);                                               \
+  } while (0)
   if (cin >= 128) {
-    torgb_kernel<32><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
-                                                              pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
+    E4S_TORGB_LAUNCH(32);
   } else if (cin >= 32) {
-    torgb_kernel<8><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
-                                                            pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
+    E4S_TORGB_LAUNCH(8);
   } else {
-    torgb_kernel<4><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w,
-                                                            pixw, pixw_sb, bias, skip, fir, rgb, accumulate);
+    E4S_TORGB_LAUNCH(4);
   }
+#undef E4S_TORGB_LAUNCH
   return check_launch("torgb");
 }
 
