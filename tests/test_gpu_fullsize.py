@@ -175,3 +175,17 @@ def test_generator_256_all_layers_masked_and_small_mask():
     assert d < 1e-3
     solo, _, _ = G([latent[1:].cuda()], None, mask[1:].cuda(), input_is_latent=True, randomize_noise=False)
     assert torch.equal(solo[0], img[1])
+
+
+@pytest.mark.parametrize("size,rl", [(128, 9), (512, 13), (512, 11)])
+def test_generator_other_sizes_vs_oracle(size, rl):
+    """Output sizes other than the two benchmarked ones: different sets of layers end up masked / un-masked (and therefore on
+    different kernels: e.g. 512^2 with rl=11 runs 256^2 un-masked with cout=128 -> fused ToRGB at three resolutions)."""
+    G, sd = _gen(size, rl, 5, seed=8)
+    latent = synth.randn(f"t{size}.{rl}.latent", (1, 12, 18, 512), 11)
+    mask = synth.onehot(synth.blocky_labels(1, 12, 512, cells=32, seed=11), 12)
+    ref, _ = orc.generator_forward(sd, size, latent, mask, split_layer_idx=5, remaining_layer_idx=rl)
+    img, _, _ = G([latent.cuda()], None, mask.cuda(), input_is_latent=True, randomize_noise=False)
+    d = float((img.cpu() - ref).abs().max())
+    print(f"{size}^2 rl={rl}: image max|diff| {d:.3e} (range {float(ref.abs().max()):.2f})")
+    assert d < 1e-3
