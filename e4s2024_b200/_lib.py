@@ -53,7 +53,7 @@ EXPORTS = [
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
-    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8",
+    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_morphology_f32",
 ]
 
 _lib = None
@@ -230,6 +230,17 @@ def tensor2im_u8(x: torch.Tensor, zero_center: bool = True) -> torch.Tensor:
     y = torch.empty(b, h, w, 3, device=x.device, dtype=torch.uint8)
     _check(lib().e4s_tensor2im_u8(_fp(x.data_ptr()), _fp(y.data_ptr()), b, h, w, int(zero_center), _stream()), "e4s_tensor2im_u8")
     return y
+
+
+def morphology(x: torch.Tensor, neighborhood: torch.Tensor, origin, border_value: float, dilate: bool) -> torch.Tensor:
+    """x [B,C,H,W] fp32, neighborhood [se_h,se_w] fp32 (see e4s_morphology_f32) -> [B,C,H,W]."""
+    _req(x), _req(neighborhood)
+    b, c, h, w = x.shape
+    se_h, se_w = neighborhood.shape
+    out = torch.empty_like(x)
+    _check(lib().e4s_morphology_f32(_fp(x.data_ptr()), _fp(neighborhood.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w, se_h, se_w,
+                                    int(origin[0]), int(origin[1]), C.c_float(border_value), int(dilate), _stream()), "e4s_morphology_f32")
+    return out
 
 
 def swap_comp_styles(target: torch.Tensor, source: torch.Tensor, comp_mask: int, below_face: bool) -> torch.Tensor:

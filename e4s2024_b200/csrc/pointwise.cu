@@ -549,3 +549,53 @@ extern "C" int e4s_tensor2im_u8(const float* x, uint8_t* y, int batch, int h, in
   return check_launch("tensor2im");
 }
 
+// ---- grey-scale morphology of the paste-back masks (reference utils/morphology.py:23-200, kornia-style) ----------------------
+// out[y,x] = max_{i,j} ( P[y+i, x+j] + nb[se_h-1-i][se_w-1-j] )   (dilation; nb flipped, :93-95)
+//          = min_{i,j} ( P[y+i, x+j] - nb[i][j] )                   (erosion, :184-186)
+// P = the image padded by the structuring element's origin with `border` (geodesic: -/+ max_val), nb = 0 (or the non-flat
+// element) where kernel != 0 and -max_val elsewhere.  One thread per output pixel, the element cached in shared memory.
+namespace e4s {
+template <bool DILATE>
+__global__ void __launch_bounds__(256) morphology_kernel(const float* __restrict__ x, const float* __restrict__ nb, float* __restrict__ out,
+                                                         int h, int w, int se_h, int se_w, int oy, int ox, float border, int64_t total) {
+  extern __shared__ float s_nb[];
+  for (int i = threadIdx.x; i < se_h * se_w; i += blockDim.x) s_nb[i] = nb[i];
+  __syncthreads();
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int px = (int)(idx % w);
+    const int64_t t = idx / w;
+    const int py = (int)(t % h);
+    const float* plane = x + (t / h) * (int64_t)h * w;
+    float acc = DILATE ? -INFINITY : INFINITY;
+    for (int i = 0; i < se_h; ++i) {
+      const int iy = py + i - oy;
+      const bool rowin = iy >= 0 && iy < h;
+      for (int j = 0; j < se_w; ++j) {
+        const int ix = px + j - ox;
+        const float v = (rowin && ix >= 0 && ix < w) ? __ldg(plane + (int64_t)iy * w + ix) : border;
+        if (DILATE) acc = fmaxf(acc, v + s_nb[(se_h - 1 - i) * se_w + (se_w - 1 - j)]);
+        else acc = fminf(acc, v - s_nb[i * se_w + j]);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+}  // namespace e4s
+
+extern "C" int e4s_morphology_f32(const float* x, const float* neighborhood, float* out, int64_t planes, int h, int w, int se_h, int se_w,
+                                  int origin_y, int origin_x, float border_value, int dilate, void* stream) {
+  using namespace e4s;
+  E4S_REQUIRE(x && neighborhood && out && planes > 0 && h > 0 && w > 0, "morphology: bad args");
+  E4S_REQUIRE(se_h > 0 && se_w > 0 && se_h * se_w <= 8192 && origin_y >= 0 && origin_y < se_h && origin_x >= 0 && origin_x < se_w,
+              "morphology: bad structuring element %dx%d origin (%d,%d)", se_h, se_w, origin_y, origin_x);
+  const int64_t total = planes * h * w;
+  const size_t smem = (size_t)se_h * se_w * sizeof(float);
+  if (dilate)
+    morphology_kernel<true><<<grid_for(total, 256), 256, smem, as_stream(stream)>>>(x, neighborhood, out, h, w, se_h, se_w, origin_y, origin_x,
+                                                                                  border_value, total);
+  else
+    morphology_kernel<false><<<grid_for(total, 256), 256, smem, as_stream(stream)>>>(x, neighborhood, out, h, w, se_h, se_w, origin_y, origin_x,
+                                                                                   border_value, total);
+  return check_launch("morphology");
+}
+

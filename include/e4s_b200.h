@@ -227,6 +227,13 @@ int e4s_swap_comp_styles_f32(const float* target, const float* source, float* ou
  * (v+1)/2 when zero_center, clamp [0,1], *255, truncate (the reference's float32 numpy arithmetic: identical bytes) */
 int e4s_tensor2im_u8(const float* x, uint8_t* y, int batch, int h, int w, int zero_center, void* stream);
 
+/* Grey-scale dilation / erosion of NCHW planes (reference utils/morphology.py:23-200): x, out [planes, h, w] fp32; neighborhood
+ * [se_h, se_w] = 0 (or the non-flat structuring element) where the kernel is non-zero and -max_val elsewhere; out-of-image taps
+ * read border_value (geodesic border: -max_val for dilation, +max_val for erosion).  dilate != 0: max(P + flipped neighborhood),
+ * else min(P - neighborhood). */
+int e4s_morphology_f32(const float* x, const float* neighborhood, float* out, int64_t planes, int h, int w, int se_h, int se_w,
+                       int origin_y, int origin_x, float border_value, int dilate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

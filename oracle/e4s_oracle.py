@@ -461,3 +461,30 @@ def tensor2im_u8(var: torch.Tensor, is_zero_center: bool = True) -> torch.Tensor
     v[v > 1] = 1                 # :73
     v = v * 255                  # :74
     return torch.from_numpy(v.astype("uint8"))
+
+
+def morphology(x: torch.Tensor, kernel: torch.Tensor, dilate: bool, structuring_element=None, origin=None,
+               border_type: str = "geodesic", border_value: float = 0.0, max_val: float = 1e4) -> torch.Tensor:
+    """utils/morphology.py:23-108 (dilation) / :111-200 (erosion), the `unfold` engine restated with explicit loops over the
+    structuring element (the `convolution` engine computes the same numbers)."""
+    se_h, se_w = kernel.shape
+    if origin is None:
+        origin = [se_h // 2, se_w // 2]                                  # :70-72
+    if border_type == "geodesic":                                        # :76-78 / :167-169
+        border_value = -max_val if dilate else max_val
+    pad = [origin[1], se_w - origin[1] - 1, origin[0], se_h - origin[0] - 1]
+    p = F.pad(x.float(), pad, mode="constant", value=border_value)
+    nb = torch.zeros_like(kernel, dtype=torch.float32) if structuring_element is None else structuring_element.clone().float()
+    nb[kernel == 0] = -max_val                                           # :84-89
+    h, w = x.shape[-2:]
+    out = None
+    for i in range(se_h):
+        for j in range(se_w):
+            win = p[..., i:i + h, j:j + w]
+            if dilate:
+                t = win + nb[se_h - 1 - i, se_w - 1 - j]                 # :93-95: max(unfolded + neighborhood.flip)
+                out = t if out is None else torch.maximum(out, t)
+            else:
+                t = win - nb[i, j]                                       # :184-186: min(unfolded - neighborhood)
+                out = t if out is None else torch.minimum(out, t)
+    return out

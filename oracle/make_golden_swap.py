@@ -40,3 +40,25 @@ x[0, 0, 0, :6] = torch.tensor([-1.0, 1.0, -1.5, 1.5, 0.0, 254.5 / 127.5 - 1])
 ys = np.stack([np.array(ref_tensor2im(x[i])) for i in range(x.shape[0])])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tensor2im.npz"), x=x.numpy(), y=ys)
 print("tensor2im golden", ys.shape, ys.dtype, "oracle mismatches:", int((orc.tensor2im_u8(x).numpy() != ys).sum()))
+
+# ---- morphology (utils/morphology.py): flat / holed / non-flat elements, even sizes, both engines, constant border ----------
+from utils.morphology import dilation as ref_dil, erosion as ref_ero  # noqa: E402
+
+xm = (synth.randn("morph.x", (2, 2, 19, 23), 70) > 0.3).float() * synth.randn("morph.v", (2, 2, 19, 23), 71).abs()
+cases_m = {"ones5": dict(kernel=torch.ones(5, 5)),
+           "cross3": dict(kernel=torch.tensor([[0., 1, 0], [1, 1, 1], [0, 1, 0]])),
+           "even4x6": dict(kernel=torch.ones(4, 6)),
+           "nonflat": dict(kernel=torch.ones(3, 3), structuring_element=torch.tensor([[0., 0.1, 0], [0.1, 0.3, 0.1], [0, 0.1, 0]])),
+           "const": dict(kernel=torch.ones(3, 5), border_type="constant", border_value=0.5),
+           "origin": dict(kernel=torch.ones(3, 3), origin=[0, 2])}
+arrm, worst = {"x": xm.numpy()}, 0.0
+for name, kw in cases_m.items():
+    for eng in ("unfold", "convolution"):
+        d, e = ref_dil(xm, engine=eng, **kw), ref_ero(xm, engine=eng, **kw)
+        okw = {k: v for k, v in kw.items() if k != "kernel"}
+        worst = max(worst, float((d - orc.morphology(xm, kw["kernel"], True, **okw)).abs().max()),
+                    float((e - orc.morphology(xm, kw["kernel"], False, **okw)).abs().max()))
+        if eng == "unfold":
+            arrm[name + "_dil"], arrm[name + "_ero"] = d.numpy(), e.numpy()
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "morphology.npz"), **arrm)
+print("morphology: oracle vs reference (both engines) max|diff|", worst)

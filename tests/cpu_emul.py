@@ -189,6 +189,20 @@ def labels_to_onehot(labels, k):
     return F.one_hot(labels.long(), k).permute(0, 3, 1, 2).float().contiguous()
 
 
+def morphology(x, neighborhood, origin, border_value, dilate):
+    """e4s_morphology_f32 restated with torch (window loops over the structuring element)."""
+    se_h, se_w = neighborhood.shape
+    h, w = x.shape[-2:]
+    p = F.pad(x.float(), [origin[1], se_w - origin[1] - 1, origin[0], se_h - origin[0] - 1], mode="constant", value=border_value)
+    out = None
+    for i in range(se_h):
+        for j in range(se_w):
+            win = p[..., i:i + h, j:j + w]
+            t = win + neighborhood[se_h - 1 - i, se_w - 1 - j] if dilate else win - neighborhood[i, j]
+            out = t if out is None else (torch.maximum(out, t) if dilate else torch.minimum(out, t))
+    return out.contiguous()
+
+
 def tensor2im_u8(x, zero_center=True):
     v = x.float()
     if zero_center:
@@ -329,7 +343,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
 
 
 _NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "bias_act", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
-          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
+          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
 

@@ -129,3 +129,20 @@ def test_tensor2im(golden):
     g = golden("tensor2im")
     assert int((orc.tensor2im_u8(T(g["x"])).numpy() != g["y"]).sum()) == 0
 
+
+MORPH_CASES = {"ones5": dict(kernel=torch.ones(5, 5)),
+               "cross3": dict(kernel=torch.tensor([[0., 1, 0], [1, 1, 1], [0, 1, 0]])),
+               "even4x6": dict(kernel=torch.ones(4, 6)),
+               "nonflat": dict(kernel=torch.ones(3, 3), structuring_element=torch.tensor([[0., 0.1, 0], [0.1, 0.3, 0.1], [0, 0.1, 0]])),
+               "const": dict(kernel=torch.ones(3, 5), border_type="constant", border_value=0.5),
+               "origin": dict(kernel=torch.ones(3, 3), origin=[0, 2])}
+
+
+def test_morphology(golden):
+    g = golden("morphology")
+    x = T(g["x"])
+    for name, kw in MORPH_CASES.items():
+        okw = {k: v for k, v in kw.items() if k != "kernel"}
+        close(orc.morphology(x, kw["kernel"], True, **okw), g[name + "_dil"], 0.0)
+        close(orc.morphology(x, kw["kernel"], False, **okw), g[name + "_ero"], 0.0)
+

@@ -225,3 +225,26 @@ def test_tensor2im_batch(golden, dev):
     assert y.dtype == torch.uint8 and tuple(y.shape) == g["y"].shape
     assert int((y.cpu().numpy() != g["y"]).sum()) == 0
 
+
+MORPH_CASES = {"ones5": dict(kernel=torch.ones(5, 5)),
+               "cross3": dict(kernel=torch.tensor([[0., 1, 0], [1, 1, 1], [0, 1, 0]])),
+               "even4x6": dict(kernel=torch.ones(4, 6)),
+               "nonflat": dict(kernel=torch.ones(3, 3), structuring_element=torch.tensor([[0., 0.1, 0], [0.1, 0.3, 0.1], [0, 0.1, 0]])),
+               "const": dict(kernel=torch.ones(3, 5), border_type="constant", border_value=0.5),
+               "origin": dict(kernel=torch.ones(3, 3), origin=[0, 2])}
+
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_morphology(golden, dev):
+    """SURVEY 8f row 4 (first piece): dilation / erosion / opening of the paste-back masks, bit-exact vs the reference functions."""
+    from e4s2024_b200.utils import morphology as M
+    g = golden("morphology")
+    with ctx_for(dev):
+        x = to(dev, T(g["x"]))
+        for name, kw in MORPH_CASES.items():
+            kw = {k: (to(dev, v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+            assert maxdiff(M.dilation(x, **kw), g[name + "_dil"]) == 0.0, name
+            assert maxdiff(M.erosion(x, **kw), g[name + "_ero"]) == 0.0, name
+        k = to(dev, torch.ones(3, 3))
+        assert maxdiff(M.opening(x, k), orc.morphology(orc.morphology(T(g["x"]), torch.ones(3, 3), False), torch.ones(3, 3), True)) == 0.0
+
