@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--engine", default=None, choices=[None, "tc", "f32"], help="conv engine override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-swap-path", action="store_true", help="skip the full swap-path (parser + encoder + generator) timing")
+    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per forward (serving.GraphedGenerator) instead of launching "
+                    "every kernel from the host; measured equal on one B200 (the step is GPU-bound), so the eager path stays the default")
     ap.add_argument("--dump-layers", default=None, help="write per-conv-launch timings (JSON lines) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -260,8 +262,24 @@ def main():
     inflight = []
     out_h = torch.empty(BATCH, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory()     # what tensor2im hands the host: uint8 HWC images
 
+    # One CUDA graph per forward (serving.GraphedGenerator): the ~40 launches of a step replay as one; the eager path stays for
+    # the per-launch timing pass and --no-graph.
+    from e4s2024_b200.serving import GraphedGenerator
+    G([latent_d], None, mask_d, input_is_latent=True, randomize_noise=False)          # first forward also packs the weights
+    n0 = L.launch_count()
+    G([latent_d], None, mask_d, input_is_latent=True, randomize_noise=False)
+    launches_per_forward = L.launch_count() - n0
+    gg = None if not args.graph else GraphedGenerator(G, BATCH, K, (mask_d.shape[2], mask_d.shape[3]), device=dev)
+
+    def gen(lat, msk):
+        if gg is None:
+            return G([lat], None, msk, input_is_latent=True, randomize_noise=False)[0]
+        return gg(lat, msk)
+
     def step_resident():
-        img, _, _ = G([latent_d], None, mask_d, input_is_latent=True, randomize_noise=False)
+        img = gen(latent_d, mask_d)
+        if world > 1 and gg is not None:
+            img = img.clone()                            # the graph's static output is overwritten by the next replay
         if world > 1:
             if len(inflight) == 2:                       # the buffer about to be reused: its gather must have completed
                 inflight.pop(0).wait()
@@ -287,7 +305,7 @@ def main():
     labels_h = mask_h.argmax(1, keepdim=True).to(torch.uint8).pin_memory()          # [B,1,512,512]
 
     def e2e_fn(lat, lab):
-        return tensor2im_batch(G([lat], None, labelMap2OneHot(lab, K), input_is_latent=True, randomize_noise=False)[0])
+        return tensor2im_batch(gen(lat, labelMap2OneHot(lab, K)))
 
     pipe = HostPipeline(e2e_fn, dev)
 
@@ -322,9 +340,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    n0 = L.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = L.launch_count() - n0
+    launches = args.steps * launches_per_forward         # kernels executed per step (a graph replay runs the same nodes)
     clocks = sampler.stop() if rank == 0 else None
     value = world * BATCH * args.steps / (ms / 1e3)
 
@@ -379,7 +396,7 @@ def main():
 
     swap = None
     if rank == 0 and world == 1 and not args.no_swap_path:
-        del G, pipe
+        del G, pipe, gg
         torch.cuda.empty_cache()
         try:
             swap = swap_path_line(dev)
@@ -392,7 +409,7 @@ def main():
                 "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if E.conv_engine() == "tc" else "f32",
                 "data": "synthetic",
                 "config": bench_config(world, E.conv_engine()),
-                "clocks": clocks, "gpu_launches": int(launches),
+                "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": gg is not None,
                 "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e / args.steps,
                         "note": "labelMap2OneHot + Generator.forward + tensor2im_batch through HostPipeline: pinned-host H2D of every step's latent + u8 "
                                 "label map, D2H of its uint8 HWC images (the reference pipelines' tensor2im output), double-buffered on copy "

@@ -327,7 +327,7 @@ class RegionCtx:
     `job_keys` = [(hout, wout, up2)] of the masked 3x3 layers whose geometry the halo kernel takes: their
     per-tile region job lists are built here and the counts come back in the same (single) D2H read as the flag."""
 
-    def __init__(self, mask: torch.Tensor, job_keys=(), lazy: bool = False):
+    def __init__(self, mask: torch.Tensor, job_keys=(), lazy: bool = False, host_flag: Optional[torch.Tensor] = None):
         """lazy=True (Generator.forward): nothing is read back while the forward is being enqueued.  The mask is ASSUMED
         one-hot (checked by `verify()` after the last launch; the caller re-runs on the generic path if not) and every
         region-job decision is a device-side launch predicate."""
@@ -341,10 +341,14 @@ class RegionCtx:
         lists = [L.region_tile_jobs(self.labels, h, w, up, self.k, meta[1 + i:2 + i]) for i, (h, w, up) in enumerate(keys)]
         self.lazy = bool(lazy) and self.mask.is_cuda
         if self.lazy:
-            self._host = torch.empty(meta.shape, dtype=torch.int32, pin_memory=True)
-            self._host.copy_(meta, non_blocking=True)
-            self._ev = torch.cuda.Event()
-            self._ev.record()
+            # host_flag: a pre-allocated pinned int32 buffer (CUDA-graph capture: nothing may be allocated on the host or waited
+            # for inside the captured region; the caller reads host_flag[0] after the replay has completed)
+            self._host = host_flag if host_flag is not None else torch.empty(meta.shape, dtype=torch.int32, pin_memory=True)
+            self._host[:meta.numel()].copy_(meta, non_blocking=True)
+            self._ev = None
+            if host_flag is None:
+                self._ev = torch.cuda.Event()
+                self._ev.record()
             host = None
             self.onehot = True                          # speculation; see verify()
         else:
@@ -361,7 +365,7 @@ class RegionCtx:
 
     def verify(self) -> bool:
         """lazy contexts: was the one-hot assumption right?  (waits only for the tiny copy issued before the first layer)"""
-        if not self.lazy:
+        if not self.lazy or self._ev is None:           # graph capture: the owner of host_flag checks it after the replay
             return True
         self._ev.synchronize()
         return int(self._host[0]) == 0

@@ -76,3 +76,49 @@ class HostPipeline:
             self._run_one()
         self.s_out.synchronize()
         torch.cuda.current_stream(self.dev).synchronize()
+
+
+class GraphedGenerator:
+    """One CUDA graph of `Generator.forward` for a fixed (batch, regions, mask size): ~40 kernel launches, the label / job-list
+    kernels and the style-table GEMMs replay as ONE launch from the host.  Possible because a forward contains no host wait: the
+    region-job decisions are device-side launch predicates and the one-hot check of the mask is read AFTER the replay.
+
+        gg = GraphedGenerator(G, batch=16, regions=12, mask_hw=(512, 512))
+        img = gg(latent, mask)        # img is the graph's static output buffer: consume (or copy) it before the next call
+
+    Noise: the registered buffers (`randomize_noise=False`), as the swap pipelines run the generator."""
+
+    def __init__(self, G, batch: int, regions: int, mask_hw=(512, 512), device: Optional[torch.device] = None, warmup: int = 2):
+        dev = device or next(G.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedGenerator needs a CUDA device (there is no CPU path)")
+        self.G = G
+        self.latent = torch.zeros(batch, regions, G.n_latent, G.style_dim, device=dev)
+        self.mask = torch.zeros(batch, regions, *mask_hw, device=dev)
+        self.mask[:, 0] = 1.0                                        # a valid one-hot mask for the warm-up / capture runs
+        self.flag = torch.zeros(16, dtype=torch.int32).pin_memory()  # [0] = "mask was not one-hot" count, written by every replay
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                                # warm-up off the default stream: packs weights, sets attributes
+            for _ in range(warmup):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.image, self.feats = self._run()
+
+    def _run(self):
+        img, _, feats = self.G([self.latent], None, self.mask, input_is_latent=True, randomize_noise=False, _host_flag=self.flag)
+        return img, feats
+
+    def __call__(self, latent: torch.Tensor, mask: torch.Tensor, check: bool = False) -> torch.Tensor:
+        self.latent.copy_(latent[:, :, :self.latent.shape[2]], non_blocking=True)    # like forward: extra W+ layers are ignored
+        self.mask.copy_(mask, non_blocking=True)
+        self.graph.replay()
+        if check:                                                    # optional: waits for the replay
+            torch.cuda.current_stream(self.latent.device).synchronize()
+            if int(self.flag[0]) != 0:
+                raise RuntimeError("GraphedGenerator: the mask is not one-hot; use Generator.forward (generic per-region path)")
+        return self.image
+

@@ -421,7 +421,7 @@ class Generator(nn.Module):
     @torch.no_grad()
     def forward(self, styles, structure_feats, mask, return_latents=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
-                use_structure_code=False, _ctx=None):
+                use_structure_code=False, _ctx=None, _host_flag=None):
         if not input_is_latent:
             styles = [self.style(s) for s in styles]
         if noise is None:
@@ -439,7 +439,7 @@ class Generator(nn.Module):
             raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
         # lazy region context: no device->host read while the layers are being enqueued (the one-hot assumption is checked
         # after the last launch; a soft / overlapping mask re-runs the forward on the generic per-region path)
-        ctx = _ctx if _ctx is not None else E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=True)
+        ctx = _ctx if _ctx is not None else E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=True, host_flag=_host_flag)
         if ctx.k != k or ctx.mask.shape[0] != b:
             raise L.E4SError("mask and latent disagree on batch / number of regions")
 

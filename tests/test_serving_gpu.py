@@ -31,3 +31,23 @@ def test_host_pipeline_bit_exact():
     for lat, msk, out in batches:
         ref = fn(lat.cuda(), msk.cuda()).cpu()
         assert torch.equal(out, ref)
+
+
+def test_graphed_generator_bit_exact():
+    """One CUDA graph of the whole forward replays to exactly the eager result, for several inputs."""
+    from e4s2024_b200.serving import GraphedGenerator
+    from e4s2024_b200.stylegan2.model import Generator
+    G = Generator(256, 512, 8, split_layer_idx=5, remaining_layer_idx=9)
+    synth.synth_module_weights(G, seed=6)
+    G = G.cuda().eval()
+    gg = GraphedGenerator(G, batch=2, regions=12, mask_hw=(512, 512))
+    for i in range(3):
+        lat = synth.randn(f"graph.latent{i}", (2, 12, 18, 512), 80 + i).cuda()
+        msk = synth.onehot(synth.blocky_labels(2, 12, 512, cells=32, seed=80 + i), 12).cuda()
+        out = gg(lat, msk, check=True).clone()
+        ref = G([lat], None, msk, input_is_latent=True, randomize_noise=False)[0]
+        assert torch.equal(out, ref), float((out - ref).abs().max())
+    soft = msk.clone()
+    soft[:, :, :8, :8] = 0.25                                        # not one-hot: the graph must refuse, not return a wrong image
+    with pytest.raises(RuntimeError):
+        gg(lat, soft, check=True)
