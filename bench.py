@@ -394,6 +394,7 @@ def main():
                         "the poly-phase up-convs execute 4x the algorithmic MACs (executed_tflops counts the latter, not the split)",
                 "by_engine": {k: {"ms": v["ms"], "launches": v["n"], "alg_tflops": v["alg"] / (v["ms"] * 1e-3) / 1e12} for k, v in by.items()}}
 
+    used_graph = gg is not None
     swap = None
     if rank == 0 and world == 1 and not args.no_swap_path:
         del G, pipe, gg
@@ -409,7 +410,7 @@ def main():
                 "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if E.conv_engine() == "tc" else "f32",
                 "data": "synthetic",
                 "config": bench_config(world, E.conv_engine()),
-                "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": gg is not None,
+                "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": used_graph,
                 "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e / args.steps,
                         "note": "labelMap2OneHot + Generator.forward + tensor2im_batch through HostPipeline: pinned-host H2D of every step's latent + u8 "
                                 "label map, D2H of its uint8 HWC images (the reference pipelines' tensor2im output), double-buffered on copy "
