@@ -49,6 +49,7 @@ class E4SConv(C.Structure):
 EXPORTS = [
     "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs",
     "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_bias_act_grad_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
@@ -160,6 +161,32 @@ def upfirdn2d(x: torch.Tensor, kernel: torch.Tensor, up: int, down: int, pad0: i
     _check(lib().e4s_upfirdn2d_f32(_fp(x.data_ptr()), _fp(kernel.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w,
                                    kh, kw, up, up, down, down, pad0, pad1, pad0, pad1, _stream()), "e4s_upfirdn2d_f32")
     return out
+
+
+def upfirdn2d_general(x: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int, down_x: int, down_y: int,
+                      pad_x0: int, pad_x1: int, pad_y0: int, pad_y1: int) -> torch.Tensor:
+    """The full parameter set of the reference op (upfirdn2d.cpp:12-23): separate x/y factors and the four pads."""
+    _req(x), _req(kernel)
+    b, c, h, w = x.shape
+    kh, kw = kernel.shape
+    oh = (h * up_y + pad_y0 + pad_y1 - kh + down_y) // down_y
+    ow = (w * up_x + pad_x0 + pad_x1 - kw + down_x) // down_x
+    out = torch.empty(b, c, max(oh, 0), max(ow, 0), device=x.device, dtype=x.dtype)
+    _check(lib().e4s_upfirdn2d_f32(_fp(x.data_ptr()), _fp(kernel.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w,
+                                   kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, _stream()), "e4s_upfirdn2d_f32")
+    return out
+
+
+def bias_act_grad(g: torch.Tensor, bias: Optional[torch.Tensor], ref: torch.Tensor, slope: float, scale: float) -> torch.Tensor:
+    _req(g), _req(ref)
+    y = torch.empty_like(g)
+    channels = g.shape[1] if g.ndim > 1 else 1
+    inner = 1
+    for d in g.shape[2:]:
+        inner *= d
+    _check(lib().e4s_bias_act_grad_f32(_fp(g.data_ptr()), _fp(_p(bias)), _fp(ref.data_ptr()), _fp(y.data_ptr()), C.c_int64(g.numel()),
+                                       C.c_int64(inner), channels, _f32(slope), _f32(scale), _stream()), "e4s_bias_act_grad_f32")
+    return y
 
 
 def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], slope: float, scale: float) -> torch.Tensor:

@@ -599,3 +599,25 @@ extern "C" int e4s_morphology_f32(const float* x, const float* neighborhood, flo
   return check_launch("morphology");
 }
 
+// ---- gradient of the fused bias + leaky ReLU (reference fused_bias_act_kernel.cu:26-47, act = 3, grad = 1) ---------------------
+// y = ((g + bias?) taken with slope where the forward OUTPUT ref was <= 0) * scale; used for grad_input (bias = NULL) and for the
+// second-order term (reference op/fused_act.py:18-47).
+namespace e4s {
+__global__ void bias_act_grad_kernel(const float* __restrict__ g, const float* __restrict__ bias, const float* __restrict__ ref,
+                                     float* __restrict__ y, int64_t n, int64_t inner, int channels, float slope, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i];
+    if (bias) v += __ldg(bias + (i / inner) % channels);
+    y[i] = (ref[i] > 0.f ? v : v * slope) * scale;
+  }
+}
+}  // namespace e4s
+
+extern "C" int e4s_bias_act_grad_f32(const float* g, const float* bias, const float* ref, float* y, int64_t n, int64_t inner, int channels,
+                                     float slope, float scale, void* stream) {
+  using namespace e4s;
+  E4S_REQUIRE(g && ref && y && n > 0 && inner > 0 && channels > 0, "bias_act_grad: bad args");
+  bias_act_grad_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(g, bias, ref, y, n, inner, channels, slope, scale);
+  return check_launch("bias_act_grad");
+}
+

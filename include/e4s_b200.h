@@ -150,6 +150,11 @@ int e4s_upfirdn2d_f32(const float* x, const float* kernel, float* out, int64_t p
 int e4s_bias_act_f32(const float* x, const float* bias, float* y, int64_t n, int64_t inner, int channels,
                      float slope, float scale, void* stream);
 
+/* gradient form of e4s_bias_act_f32 (reference fused_bias_act_kernel.cu act=3, grad=1): y[i] = (ref[i] > 0 ? v : v*slope) * scale with
+ * v = g[i] + bias[channel] (bias may be NULL); ref = the forward output.  Used by the autograd of fused_leaky_relu (op/fused_act.py:18-69). */
+int e4s_bias_act_grad_f32(const float* g, const float* bias, const float* ref, float* y, int64_t n, int64_t inner, int channels,
+                          float slope, float scale, void* stream);
+
 /* NHWC noise+bias+leaky-relu for the generic-mask path: y = lrelu(x + nw*noise + bias[c]) * scale, in place ok */
 int e4s_noise_bias_act_nhwc_f32(float* x, int batch, int h, int w, int c, const float* noise, const float* noise_w,
                                 int64_t noise_sb, int64_t noise_sc, const float* bias, float slope, float scale,

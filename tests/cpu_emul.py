@@ -145,6 +145,26 @@ def upfirdn2d(x, kernel, up, down, pad0, pad1):
     return orc.upfirdn2d(x, kernel, up, down, (pad0, pad1)).contiguous()
 
 
+def upfirdn2d_general(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    """e4s_upfirdn2d_f32 with its full parameter set: zero-insert, pad / crop per side, correlate with the flipped kernel, decimate."""
+    b, c, h, w = x.shape
+    kh, kw = kernel.shape
+    z = x.new_zeros(b, c, h * up_y, w * up_x)
+    z[:, :, ::up_y, ::up_x] = x
+    z = F.pad(z, [max(pad_x0, 0), max(pad_x1, 0), max(pad_y0, 0), max(pad_y1, 0)])
+    z = z[:, :, max(-pad_y0, 0): z.shape[2] - max(-pad_y1, 0), max(-pad_x0, 0): z.shape[3] - max(-pad_x1, 0)]
+    wt = torch.flip(kernel.to(x.dtype), [0, 1]).reshape(1, 1, kh, kw)
+    hh, ww = z.shape[2], z.shape[3]
+    y = F.conv2d(z.reshape(b * c, 1, hh, ww), wt).reshape(b, c, hh - kh + 1, ww - kw + 1)
+    return y[:, :, ::down_y, ::down_x].contiguous()
+
+
+def bias_act_grad(g, bias, ref, slope, scale):
+    shape = [1, -1] + [1] * (g.ndim - 2)
+    v = g if bias is None else g + bias.reshape(shape)
+    return torch.where(ref > 0, v, v * slope) * scale
+
+
 def bias_act(x, bias, slope, scale):
     shape = [1, -1] + [1] * (x.ndim - 2)
     v = x if bias is None else x + bias.reshape(shape)
@@ -342,7 +362,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
     return nchw_to_nhwc(y, c_pad)
 
 
-_NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "bias_act", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
+_NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "upfirdn2d_general", "bias_act", "bias_act_grad", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
           "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
@@ -355,8 +375,10 @@ def emulated():
     g = globals()
     for n in _NAMES:
         setattr(L, n, g[n])
+    L.EMULATED = True                       # lets the public op functions accept CPU tensors for the duration of the test
     try:
         yield
     finally:
+        L.EMULATED = False
         for n, f in saved.items():
             setattr(L, n, f)

@@ -70,7 +70,7 @@ def test_ops_public_api_cuda(golden):
     assert maxdiff(fused_leaky_relu(T(f["x"]).cuda(), T(f["bias"]).cuda()), f["y"]) < 1e-6
     m = FusedLeakyReLU(6).cuda()
     m.bias.data.copy_(T(f["bias"]))
-    assert maxdiff(m(T(f["x"]).cuda()), f["y"]) < 1e-6
+    assert maxdiff(m(T(f["x"]).cuda()).detach(), f["y"]) < 1e-6
     with pytest.raises(RuntimeError):
         fused_leaky_relu(T(f["x"]), T(f["bias"]))          # CPU tensors are rejected, like the reference op
 
@@ -247,4 +247,47 @@ def test_morphology(golden, dev):
             assert maxdiff(M.erosion(x, **kw), g[name + "_ero"]) == 0.0, name
         k = to(dev, torch.ones(3, 3))
         assert maxdiff(M.opening(x, k), orc.morphology(orc.morphology(T(g["x"]), torch.ones(3, 3), False), torch.ones(3, 3), True)) == 0.0
+
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_ops_autograd(dev):
+    """upfirdn2d / fused_leaky_relu are differentiable like the reference ops (op/upfirdn2d.py:17-139, op/fused_act.py:18-69):
+    first-order gradients and a second-order term against torch autograd through the oracle's pure-torch restatement."""
+    from e4s2024_b200.stylegan2.op import fused_leaky_relu, upfirdn2d
+    k4 = torch.tensor([1., 3., 3., 1.])
+    k4 = torch.outer(k4, k4) / 64
+    cases = [dict(kernel=k4 * 4, up=2, down=1, pad=(2, 1)), dict(kernel=k4 * 4, up=1, down=1, pad=(1, 1)),
+             dict(kernel=k4, up=1, down=2, pad=(1, 1)), dict(kernel=torch.tensor([[1., 2., 1.], [0., 1., 3.]]) / 8, up=2, down=3, pad=(3, 0))]
+    with ctx_for(dev):
+        for i, kw in enumerate(cases):
+            x0 = synth.randn(f"ag.up.x{i}", (2, 3, 9, 11), 90 + i)
+            xr = x0.clone().requires_grad_(True)
+            yr = orc.upfirdn2d(xr, kw["kernel"], kw["up"], kw["down"], kw["pad"])
+            gy = synth.randn(f"ag.up.g{i}", tuple(yr.shape), 95 + i)
+            (gr,) = torch.autograd.grad(yr, xr, gy)
+            v = synth.randn(f"ag.up.v{i}", tuple(x0.shape), 99 + i)
+            x = to(dev, x0).requires_grad_(True)
+            gyd = to(dev, gy).requires_grad_(True)
+            y = upfirdn2d(x, to(dev, kw["kernel"]), up=kw["up"], down=kw["down"], pad=kw["pad"])
+            assert maxdiff(y.detach(), yr.detach()) < 1e-5
+            (g,) = torch.autograd.grad(y, x, gyd, create_graph=True)
+            assert maxdiff(g.detach(), gr.detach()) < 1e-5, i
+            # second order: d<g, v>/d(gy) = upfirdn2d(v) -- the gradient is linear in gy
+            (gg,) = torch.autograd.grad(g, gyd, to(dev, v))
+            assert maxdiff(gg, orc.upfirdn2d(v, kw["kernel"], kw["up"], kw["down"], kw["pad"])) < 1e-5, i
+        # fused_leaky_relu: grad wrt input and bias, and the second-order term wrt the incoming gradient
+        x0 = synth.randn("ag.flr.x", (2, 6, 5, 7), 110)
+        b0 = synth.randn("ag.flr.b", (6,), 111, 0.5)
+        gy0 = synth.randn("ag.flr.g", (2, 6, 5, 7), 112)
+        xr, br = x0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        yr = orc.fused_leaky_relu(xr, br)
+        gxr, gbr = torch.autograd.grad(yr, (xr, br), gy0)
+        x, b, gy = to(dev, x0).requires_grad_(True), to(dev, b0).requires_grad_(True), to(dev, gy0).requires_grad_(True)
+        y = fused_leaky_relu(x, b)
+        gx, gb = torch.autograd.grad(y, (x, b), gy, create_graph=True)
+        assert maxdiff(gx.detach(), gxr) < 1e-6 and maxdiff(gb.detach(), gbr) < 1e-5
+        vx, vb = to(dev, synth.randn("ag.flr.vx", (2, 6, 5, 7), 113)), to(dev, synth.randn("ag.flr.vb", (6,), 114))
+        (gg,) = torch.autograd.grad((gx, gb), gy, (vx, vb))
+        ref = torch.where(yr.detach() > 0, 1.0, 0.2) * 2 ** 0.5 * (vx.cpu() + vb.cpu().reshape(1, -1, 1, 1))
+        assert maxdiff(gg, ref) < 1e-6
 
