@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libe4s_b200.so")
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_PRELU, ACT_SIGMOID, ACT_RSQRT_EPS = range(6)
+TC_BF16, TC_F16 = 0, 1
 CONV_NORMAL, CONV_UP2 = 0, 1
 
 _fp = C.c_void_p
@@ -43,18 +44,19 @@ class E4SConv(C.Structure):
         ("out", _fp), ("out_pitch", _i64), ("accumulate", _i32),
         ("rgb", _fp), ("rgb_w", _fp), ("rgb_smod", _fp), ("rgb_bias", _fp), ("rgb_skip", _fp), ("rgb_fir", _fp),
         ("pred_count", _fp), ("pred_limit", _i32), ("pred_run_if_gt", _i32),
+        ("tc_fmt", _i32), ("tc_out_scale", _f32), ("tc_unbias", _f32),
     ]
 
 
 EXPORTS = [
     "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs",
-    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_pack_weights_tc_fmt", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_bias_act_grad_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
-    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_morphology_f32",
+    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_im2tensor_f32", "e4s_morphology_f32",
 ]
 
 _lib = None
@@ -141,13 +143,14 @@ def conv_batched(params_list):
     _check(lib().e4s_conv_f32_batched(arr, n, _stream()), "e4s_conv_f32_batched")
 
 
-def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cin: int, cout: int, cout_pad: int) -> torch.Tensor:
+def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cin: int, cout: int, cout_pad: int, fmt: int = TC_BF16,
+                    scale: float = 1.0) -> torch.Tensor:
     nbytes = int(lib().e4s_pack_weights_tc_bytes(phases, k, cout))
     if nbytes <= 0:
         raise E4SError("e4s_pack_weights_tc_bytes: unsupported shape")
     out = torch.empty(nbytes, dtype=torch.uint8, device=w_f32.device)
-    _check(lib().e4s_pack_weights_tc(C.c_void_p(w_f32.data_ptr()), phases, k, cin, cout, cout_pad, C.c_void_p(out.data_ptr()),
-                                     _stream()), "e4s_pack_weights_tc")
+    _check(lib().e4s_pack_weights_tc_fmt(C.c_void_p(w_f32.data_ptr()), phases, k, cin, cout, cout_pad, int(fmt), _f32(scale),
+                                         C.c_void_p(out.data_ptr()), _stream()), "e4s_pack_weights_tc_fmt")
     return out
 
 
@@ -257,6 +260,19 @@ def tensor2im_u8(x: torch.Tensor, zero_center: bool = True) -> torch.Tensor:
     y = torch.empty(b, h, w, 3, device=x.device, dtype=torch.uint8)
     _check(lib().e4s_tensor2im_u8(_fp(x.data_ptr()), _fp(y.data_ptr()), b, h, w, int(zero_center), _stream()), "e4s_tensor2im_u8")
     return y
+
+
+def im2tensor(x: torch.Tensor, want01: bool = True, want_norm: bool = True, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    """u8 HWC [B,H,W,3] on the device -> (x01 [B,3,H,W] or None, xnorm [B,3,H,W] or None), fp32 (TO_TENSOR / NORMALIZE)."""
+    _req(x, torch.uint8)
+    b, h, w, c = x.shape
+    if c != 3:
+        raise E4SError("im2tensor expects [B,H,W,3]")
+    y01 = torch.empty(b, 3, h, w, device=x.device, dtype=torch.float32) if want01 else None
+    yn = torch.empty(b, 3, h, w, device=x.device, dtype=torch.float32) if want_norm else None
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _check(lib().e4s_im2tensor_f32(_fp(x.data_ptr()), _fp(_p(y01)), _fp(_p(yn)), b, h, w, m3, s3, _stream()), "e4s_im2tensor_f32")
+    return y01, yn
 
 
 def morphology(x: torch.Tensor, neighborhood: torch.Tensor, origin, border_value: float, dilate: bool) -> torch.Tensor:

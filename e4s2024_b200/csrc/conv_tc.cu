@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   constexpr int STAGES = tc_stages(BN);
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = tc_stage_bytes(BN);
-  constexpr uint32_t IDESC = umma_idesc(BN);
+  const uint32_t IDESC = umma_idesc_fmt(umma_idesc(BN), p.tc_fmt);
+  const bool f16 = p.tc_fmt == E4S_TC_F16;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), 2 * BN);   // [main | small-term accumulator of the fp16 mode]
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -221,13 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = f[2 * j], b = f[2 * j + 1];
-          const uint32_t h = pack_bf16x2(a, b);
-          const float ah = __uint_as_float(h << 16), bh = __uint_as_float(h & 0xffff0000u);
-          hi[j] = h;
-          lo[j] = pack_bf16x2(a - ah, b - bh);
-        }
+        for (int j = 0; j < 4; ++j) tc_split2(f16, f[2 * j], f[2 * j + 1], hi[j], lo[j]);
         const uint32_t off = row * 128 + ((cg ^ (row & 7)) << 4);   // 128B swizzle: 16B chunk index ^= row % 8
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -255,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       int sy = nearest_src(rw.oy, p.lab_h, p.hout), sx = nearest_src(rw.ox, p.lab_w, p.wout);
       pw = __ldg(p.pixw + (int64_t)rw.b * p.pixw_sb + (int64_t)sy * p.lab_w + sx);
     }
-    const float corr = tc_acc_unbias(num_kc * (TC_BK / 16) * 3);      // 3 accumulating MMAs per K step of 16
+    const float corr = tc_acc_unbias(p, num_kc * (TC_BK / 16) * (f16 ? 1 : 3));   // accumulate steps into the main accumulator      // 3 accumulating MMAs per K step of 16
     TcEpiRow er;
     er.pix = pix;
     er.drow = drow;
@@ -295,6 +290,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
           }
         }
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+        if (f16) {
+          float acc2[16];
+          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + half * (BN / 2) + c0), acc2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(acc2[j], 1.f / TC_LO_SCALE, acc[j]);
+        }
         if (live) {
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
@@ -312,6 +313,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       for (int c0 = 0; c0 < BN / 2; c0 += 16) {
         float acc[16];
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+        if (f16) {
+          float acc2[16];
+          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + half * (BN / 2) + c0), acc2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(acc2[j], 1.f / TC_LO_SCALE, acc[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] *= corr;
         if (live) tc_epilogue16(p, acc, n_base + c0, er);
@@ -334,9 +341,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
             const uint32_t koff = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
             const uint64_t dah = umma_smem_desc(a_hi + koff), dal = umma_smem_desc(a_lo + koff);
             const uint64_t dbh = umma_smem_desc(b_hi + koff), dbl = umma_smem_desc(b_lo + koff);
-            umma_bf16(tmem_acc, dal, dbh, IDESC, (kc | k) != 0);   // small terms first
-            umma_bf16(tmem_acc, dah, dbl, IDESC, 1);
-            umma_bf16(tmem_acc, dah, dbh, IDESC, 1);
+            if (f16) {                                             // separate accumulator for the small terms (tc_ptx.cuh)
+              umma_bf16(tmem_acc + BN, dal, dbh, IDESC, (kc | k) != 0);
+              umma_bf16(tmem_acc + BN, dah, dbl, IDESC, 1);
+              umma_bf16(tmem_acc, dah, dbh, IDESC, (kc | k) != 0);
+            } else {
+              umma_bf16(tmem_acc, dal, dbh, IDESC, (kc | k) != 0);   // small terms first
+              umma_bf16(tmem_acc, dah, dbl, IDESC, 1);
+              umma_bf16(tmem_acc, dah, dbh, IDESC, 1);
+            }
           }
           umma_commit(bar_empty + 8 * s);          // frees this smem stage once the MMAs above have read it
         }
@@ -373,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   __syncthreads();
   if (warp == TC_PRODUCER_WARPS) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_acc, 2 * BN);
   }
 }
 
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
 // image.  Phase-inner, so a kernel that merges the phases of an up-convolution along N (halo: PM = 4, wide: slot pairs)
 // fetches a whole K chunk with ONE bulk copy; a single phase is two copies (hi, lo).
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int phases, int K, int cin, int cout, int cout_pad, int bn,
-                                       uint8_t* __restrict__ out, int64_t total) {
+                                       uint8_t* __restrict__ out, int64_t total, const int fmt, const float wscale) {
   const int num_kc = (K + TC_BK - 1) / TC_BK, nt = cout / bn;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // i enumerates (phase, n_tile, kc, n_local, kpair) with kpair = 32 bf16 pairs per row
@@ -403,10 +416,10 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int phases, 
     } else {
       k = kc * TC_BK + kp * 2;
     }
-    const float a = k < K ? w[((int64_t)ph * K + k) * cout_pad + n] : 0.f;
-    const float b = k + 1 < K ? w[((int64_t)ph * K + k + 1) * cout_pad + n] : 0.f;
-    const uint32_t h = pack_bf16x2(a, b);
-    const uint32_t l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
+    const float a = k < K ? w[((int64_t)ph * K + k) * cout_pad + n] * wscale : 0.f;      // wscale is a power of two: exact
+    const float b = k + 1 < K ? w[((int64_t)ph * K + k + 1) * cout_pad + n] * wscale : 0.f;
+    uint32_t h, l;
+    tc_split2(fmt == E4S_TC_F16, a, b, h, l);
     const int64_t tile = (((int64_t)ntile * num_kc + kc) * phases) * (2 * (int64_t)bn * 128);     // chunk base: hi[phases] | lo[phases]
     const int chunk = (kp >> 2) ^ (nl & 7);
     const int64_t off = (int64_t)nl * 128 + chunk * 16 + (kp & 3) * 4;
@@ -457,7 +470,13 @@ extern "C" int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout) {
 }
 
 extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, void* w_packed, void* stream) {
+  return e4s_pack_weights_tc_fmt(w_f32, phases, k, cin, cout, cout_pad, E4S_TC_BF16, 1.f, w_packed, stream);
+}
+
+extern "C" int e4s_pack_weights_tc_fmt(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, int fmt, float scale,
+                                       void* w_packed, void* stream) {
   E4S_REQUIRE(w_f32 && w_packed, "pack_weights_tc: null pointer");
+  E4S_REQUIRE((fmt == E4S_TC_BF16 || fmt == E4S_TC_F16) && scale > 0.f, "pack_weights_tc: bad operand format %d / scale %g", fmt, (double)scale);
   E4S_REQUIRE(phases >= 1 && tc_shape_ok(k, cout) && cout_pad >= cout, "pack_weights_tc: unsupported shape K=%d cout=%d", k, cout);
   E4S_REQUIRE(cin >= 8 && cin % 8 == 0 && k % cin == 0, "pack_weights_tc: K=%d must be taps * cin (cin=%d)", k, cin);
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "pack_weights_tc: output must be 16-byte aligned");
@@ -465,7 +484,7 @@ extern "C" int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int ci
   const int64_t total = (int64_t)phases * (cout / bn) * ((k + TC_BK - 1) / TC_BK) * bn * 32;
   int64_t g = ceil_div64(total, 256);
   if (g > 148 * 32) g = 148 * 32;
-  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, phases, k, cin, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total);
+  pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, phases, k, cin, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total, fmt, scale);
   return check_launch("pack_weights_tc");
 }
 
@@ -476,6 +495,7 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
   const int K = p->kh * p->kw * p->cin;
   E4S_REQUIRE(tc_shape_ok(K, p->cout), "conv_tc: needs cin %% 8 == 0 and cout in {32,64,128,256*n} (cin=%d cout=%d)", p->cin, p->cout);
   E4S_REQUIRE(!p->in_square, "conv_tc: in_square is only implemented by the fp32 engine");
+  E4S_REQUIRE(p->tc_fmt == E4S_TC_BF16 || p->tc_fmt == E4S_TC_F16, "conv_tc: unknown operand format %d", p->tc_fmt);
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc: out must be 16-byte aligned with pitch %% 4 == 0");
   if (p->rgb)
     E4S_REQUIRE(tc_halo_eligible(p) && p->mode != E4S_CONV_UP2_POLYPHASE && p->cout <= 128 && tc_epi_is_fast(*p) && p->regions == 1 &&
@@ -492,12 +512,13 @@ extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream)
     const char* e = getenv("E4S_TC_HALO");
     g_tc_halo = (e && e[0] == '0') ? 0 : 1;
   }
-  if ((g_tc_halo || p->rgb) && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s, nullptr, nullptr, 0);
+  const bool f16_up = up && p->tc_fmt == E4S_TC_F16;          // the halo kernel separates the fp16 accumulators on same-resolution layers only
+  if ((g_tc_halo || p->rgb) && !f16_up && tc_halo_eligible(p)) return tc_launch_halo(p, w_packed, s, nullptr, nullptr, 0);
   if (g_tc_wide < 0) {
     const char* e = getenv("E4S_TC_WIDE");
     g_tc_wide = (e && e[0] == '0') ? 0 : 1;
   }
-  if (g_tc_wide && tc_wide_eligible(p)) return tc_launch_wide(p, w_packed, s);
+  if (g_tc_wide && p->tc_fmt == E4S_TC_BF16 && tc_wide_eligible(p)) return tc_launch_wide(p, w_packed, s);   // the wide kernel is bf16 only
   switch (tc_block_n(p->cout)) {
     case 256: return launch_tc<256>(p, w_packed, m_total, s);
     case 128: return launch_tc<128>(p, w_packed, m_total, s);
@@ -519,6 +540,8 @@ extern "C" int e4s_conv_tc_regions(const E4SConv* p, const void* w_packed, const
   const int K = p->kh * p->kw * p->cin;
   E4S_REQUIRE(tc_shape_ok(K, p->cout) && tc_halo_geometry_ok(p), "conv_tc_regions: geometry not supported by the halo kernel");
   E4S_REQUIRE(!p->in_square && !p->pixw && !p->rgb, "conv_tc_regions: in_square / pixw / fused ToRGB are not supported here");
+  E4S_REQUIRE(p->tc_fmt == E4S_TC_BF16 || (p->tc_fmt == E4S_TC_F16 && p->mode != E4S_CONV_UP2_POLYPHASE),
+              "conv_tc_regions: operand format %d is not supported for this layer", p->tc_fmt);
   E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, "conv_tc_regions: out must be 16-byte aligned");
   return tc_launch_halo(p, w_packed, as_stream(stream), reinterpret_cast<const int4*>(jobs), job_count, job_count_host);
 }

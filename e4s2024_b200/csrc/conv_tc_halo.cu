@@ -104,13 +104,16 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
   constexpr int PL = P / PM;                      // MMA groups of PM merged phases
   constexpr int BST = hl_b_stages(BN, PM);
   constexpr int STAGE_B = 2 * PM * B_BYTES;       // [hi: PM x BN rows][lo: PM x BN rows]
-  constexpr uint32_t IDESC = umma_idesc(PM * BN);
+  const uint32_t IDESC = umma_idesc_fmt(umma_idesc(PM * BN), p.tc_fmt);
+  const bool f16 = p.tc_fmt == E4S_TC_F16;
   // same-resolution layers with BN <= 64: the hi and lo weight tiles of a stage are adjacent rows of one operand, so
   // A_hi x [B_hi ; B_lo] is ONE MMA with N = 2*BN (two accumulator halves, summed in the epilogue) followed by A_lo x B_hi:
   // 2 instead of 3 MMAs per K step (an M=128 MMA costs the same ~61 cycles for every N <= 128, profiles/r1_umma_rate_experiment.txt)
   constexpr bool NC = !UP && BN <= 64;
-  constexpr uint32_t IDESC2 = umma_idesc(2 * BN <= 256 ? 2 * BN : 256);
-  constexpr int ACC_COLS = P * BN * (NC ? 2 : 1);            // TMEM columns of one accumulator set
+  const uint32_t IDESC2 = umma_idesc_fmt(umma_idesc(2 * BN <= 256 ? 2 * BN : 256), p.tc_fmt);
+  // fp16 operands (same-resolution layers only): hi*hi accumulates alone, the two small terms go to a second accumulator (tc_ptx.cuh,
+  // TC_LO_SCALE) -- for NC that is the second half the N-merged MMA already writes, otherwise BN more columns per set
+  constexpr int ACC_COLS = P * BN * (UP ? 1 : 2);            // TMEM columns of one accumulator set
   constexpr int NSETS = (2 * ACC_COLS <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = NSETS * ACC_COLS <= 32 ? 32 : NSETS * ACC_COLS <= 64 ? 64 : NSETS * ACC_COLS <= 128 ? 128 : NSETS * ACC_COLS <= 256 ? 256 : 512;
 
@@ -289,12 +292,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           }
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = f[2 * j], b = f[2 * j + 1];
-            const uint32_t h = pack_bf16x2(a, b);
-            hi[j] = h;
-            lo[j] = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
-          }
+          for (int j = 0; j < 4; ++j) tc_split2(f16, f[2 * j], f[2 * j + 1], hi[j], lo[j]);
           // 128B swizzle on ABSOLUTE shared-memory address bits [7:9] (the plane base is only 128-byte aligned)
           const uint32_t rowaddr = (uint32_t)(hs * HALO_BYTES) + px * 128;
           const uint32_t off = px * 128 + ((cg ^ ((rowaddr >> 7) & 7)) << 4);
@@ -328,7 +326,8 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
     const bool fast = tc_epi_is_fast(p) && !(dbg & (1 | 2 | 8 | 16 | 128));    // bit7: force the generic epilogue
     const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
     // accumulate steps into the main accumulator: 9 taps x ksteps per group, 3 MMAs each (2 where hi|lo weights merge along N)
-    const float corr = tc_acc_unbias(G * 9 * ksteps * (NC ? 2 : 3));
+    const float corr = tc_acc_unbias(p, G * 9 * ksteps * (f16 ? 1 : (NC ? 2 : 3)));
+    const float low = f16 ? 1.f / TC_LO_SCALE : 1.f;         // weight of the second accumulator half
     // fused ToRGB tail (host guarantees: !UP, one n-tile, no region jobs, fast epilogue)
     const bool do_rgb = !UP && p.rgb != nullptr;
     const int sk_h = p.hout >> 1, sk_w = p.wout >> 1;
@@ -431,7 +430,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           float* optr = p.out ? p.out + pix * p.out_pitch + jb.nt * BN : nullptr;
           const float nz = nw * cur.nz[ph];
           float rgb3[3] = {0.f, 0.f, 0.f};
-          if (NC) {
+          if (NC || (!UP && f16)) {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
               uint32_t ra[16], rb[16];
@@ -440,7 +439,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
               tmem_ld16_nowait(tacc + (uint32_t)(BN + c0), rb);
               tmem_wait_ld16x2(ra, rb);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+              for (int j = 0; j < 16; ++j) acc[j] = fmaf(__uint_as_float(rb[j]), low, __uint_as_float(ra[j]));
               if (live) {
                 if (do_rgb) tc_epilogue_fast<16, true>(optr ? optr + c0 : nullptr, acc, sv, c0, BN, nz, gain, sv + 3 * BN, rgb3);
                 else tc_epilogue_fast<16>(optr + c0, acc, sv, c0, BN, nz, gain);
@@ -486,11 +485,11 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
           float acc[16];
           if (!(dbg & 2)) {
             tmem_ld16(tacc + (uint32_t)c0, acc);
-            if (NC) {
+            if (NC || (!UP && f16)) {
               float acc2[16];
               tmem_ld16(tacc + (uint32_t)(BN + c0), acc2);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] += acc2[j];
+              for (int j = 0; j < 16; ++j) acc[j] = fmaf(acc2[j], low, acc[j]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] *= corr;
@@ -518,6 +517,7 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
       constexpr uint32_t A_HI = umma_desc_hi(HL_HP * 128), B_HI = umma_desc_hi(1024);
       constexpr uint32_t kb16 = (uint32_t)(cin_eff * 2) >> 4;   // 16-byte units per tap inside a packed 64-wide K chunk
       const uint32_t b_ring = umma_desc_lo(smem_base + B_OFF);
+      const uint32_t lo_col = f16 ? (uint32_t)BN : 0u;
       int hg = 0, bs = 0, bph = 0;                             // running halo-fill counter, weight stage and its phase parity
       for (int it = 0; it < my_jobs; ++it) {
         if (resident) bs = 0;                                  // resident weights: chunk i of every job lives in stage i
@@ -558,7 +558,11 @@ conv_tc_halo_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int 
                       const uint32_t first = (t9 | k) != 0 ? 1u : (uint32_t)(g != 0);
                       if (NC) {
                         umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC2, first);   // A_hi x [B_hi ; B_lo] -> both accumulator halves
-                        umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, 1);        // A_lo x B_hi        -> first half
+                        umma_bf16_w(tacc + lo_col, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, 1);   // A_lo x B_hi -> first half (fp16: second)
+                      } else if (!UP && f16) {                                              // separate small-term accumulator
+                        umma_bf16_w(tacc + BN, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, first);
+                        umma_bf16_w(tacc + BN, a_h + ao, A_HI, b_l + bo, B_HI, IDESC, 1);
+                        umma_bf16_w(tacc, a_h + ao, A_HI, b_h + bo, B_HI, IDESC, first);
                       } else {
                         umma_bf16_w(tacc, a_l + ao, A_HI, b_h + bo, B_HI, IDESC, first);
                         umma_bf16_w(tacc, a_h + ao, A_HI, b_l + bo, B_HI, IDESC, 1);

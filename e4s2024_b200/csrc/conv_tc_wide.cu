@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
     const WdRow rw = rows[q * 32 + lane];
     const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
     const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
-    const float corr = tc_acc_unbias(num_kc * 4 * 3);                 // accumulate steps per output (tc_ptx.cuh)
+    const float corr = tc_acc_unbias(p, num_kc * 4 * 3);                 // accumulate steps per output (tc_ptx.cuh)
 #pragma unroll 1
     for (int sl = 2 * hh; sl < 2 * hh + 2; ++sl) {
       const int oy = UP ? 2 * rw.y + (sl >> 1) : rw.y, ox = UP ? 2 * rw.x + (sl & 1) : rw.x;

@@ -549,6 +549,53 @@ extern "C" int e4s_tensor2im_u8(const float* x, uint8_t* y, int batch, int h, in
   return check_launch("tensor2im");
 }
 
+// ---- TO_TENSOR + NORMALIZE on the device (reference datasets/dataset.py:45, torchvision ToTensor / Normalize), batched ------------
+// u8 HWC [B,H,W,3] -> fp32 NCHW: x01 = v / 255 (what FaceParser.preprocess_img feeds the parser) and / or
+// xn = (x01 - mean[c]) / std[c] (what the pipelines feed Net3) -- the same fp32 operations in the same order, so the floats are
+// identical to the reference's.  Four pixels per thread: three u32 loads, one float4 store per plane and output.
+namespace e4s {
+__global__ void __launch_bounds__(256) im2tensor_kernel(const uint8_t* __restrict__ x, float* __restrict__ y01, float* __restrict__ yn, int64_t hw4,
+                                                        int64_t hw, float m0, float m1, float m2, float s0, float s1, float s2, int64_t total) {
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / hw4, q = i - b * hw4;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + (b * hw + q * 4) * 3);
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u,
+                             (w1 >> 16) & 255u, w1 >> 24, w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4 v;
+      v.x = __fdiv_rn((float)by[c], 255.f); v.y = __fdiv_rn((float)by[3 + c], 255.f);
+      v.z = __fdiv_rn((float)by[6 + c], 255.f); v.w = __fdiv_rn((float)by[9 + c], 255.f);
+      const int64_t o = (b * 3 + c) * hw + q * 4;
+      if (y01) *reinterpret_cast<float4*>(y01 + o) = v;
+      if (yn) {
+        float4 n;
+        n.x = __fdiv_rn(v.x - mean[c], sd[c]); n.y = __fdiv_rn(v.y - mean[c], sd[c]);
+        n.z = __fdiv_rn(v.z - mean[c], sd[c]); n.w = __fdiv_rn(v.w - mean[c], sd[c]);
+        *reinterpret_cast<float4*>(yn + o) = n;
+      }
+    }
+  }
+}
+}  // namespace e4s
+
+extern "C" int e4s_im2tensor_f32(const uint8_t* x, float* y01, float* ynorm, int batch, int h, int w, const float* mean3, const float* std3,
+                                 void* stream) {
+  using namespace e4s;
+  E4S_REQUIRE(x && (y01 || ynorm) && batch > 0 && h > 0 && w > 0, "im2tensor: bad args");
+  E4S_REQUIRE(!ynorm || (mean3 && std3), "im2tensor: ynorm needs mean3 / std3 (host arrays of 3 floats)");
+  E4S_REQUIRE(((int64_t)h * w) % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y01) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(ynorm) & 15) == 0,
+              "im2tensor: h*w must be a multiple of 4 and the buffers 4 / 16 byte aligned");
+  const int64_t hw = (int64_t)h * w, total = (int64_t)batch * (hw / 4);
+  const float m[3] = {mean3 ? mean3[0] : 0.f, mean3 ? mean3[1] : 0.f, mean3 ? mean3[2] : 0.f};
+  const float sd[3] = {std3 ? std3[0] : 1.f, std3 ? std3[1] : 1.f, std3 ? std3[2] : 1.f};
+  im2tensor_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, y01, ynorm, hw / 4, hw, m[0], m[1], m[2], sd[0], sd[1], sd[2], total);
+  return check_launch("im2tensor");
+}
+
 // ---- grey-scale morphology of the paste-back masks (reference utils/morphology.py:23-200, kornia-style) ----------------------
 // out[y,x] = max_{i,j} ( P[y+i, x+j] + nb[se_h-1-i][se_w-1-j] )   (dilation; nb flipped, :93-95)
 //          = min_{i,j} ( P[y+i, x+j] - nb[i][j] )                   (erosion, :184-186)

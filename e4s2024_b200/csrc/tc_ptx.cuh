@@ -1,6 +1,7 @@
 // PTX wrappers and tile constants shared by the tcgen05 convolution kernels (conv_tc.cu, conv_tc_halo.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -251,6 +252,38 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// The 3-pass operand split v = hi + lo of two consecutive K elements (a = lower address), as two packed 16-bit pairs.
+//   bf16 (E4S_TC_BF16): 8 + 8 mantissa bits, fp32 exponent range  -> 2^-17 relative per operand
+//   fp16 (E4S_TC_F16):  11 + 11 mantissa bits, |v| <= 65504 (clamped; lo parts below 2^-14 fall into the fp16 subnormals,
+//                       absolute resolution 2^-25)                    -> 2^-22 relative per operand: fp32 class
+// Both run as tcgen05.mma kind::f16 at the same rate; only the a/b format bits of the instruction descriptor differ.
+//
+// fp16 mode also SEPARATES the accumulators (TC_LO_SCALE): the tensor core truncates every product to the accumulator's ulp when
+// it aligns the addends, so adding the 2^-11-sized hi*lo / lo*hi terms into the main accumulator costs two more ulp-sized
+// truncations per element (measured: 3.4x the error of an fp32 FMA chain at K = 4608 although the operands are exact to 2^-22).
+// Here hi*hi accumulates alone and the two small terms go to a second TMEM accumulator whose truncation unit is 2^-11 of the
+// main one's; the lo parts are stored multiplied by 2^11 (never subnormal when hi is normal) and the epilogue adds
+// small * 2^-11 to the main sum in fp32.
+constexpr float TC_LO_SCALE = 2048.f;
+__device__ __forceinline__ void tc_split2(const bool f16, const float a, const float b, uint32_t& hi, uint32_t& lo) {
+  if (f16) {
+    const float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(ac, bc);                 // .x (low 16 bits) = a
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn((ac - back.x) * TC_LO_SCALE, (bc - back.y) * TC_LO_SCALE);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const uint32_t h = pack_bf16x2(a, b);
+    hi = h;
+    lo = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
+  }
+}
+// instruction-descriptor a/b format fields: 1 = bf16 (what umma_idesc sets), 0 = fp16
+__host__ __device__ __forceinline__ uint32_t umma_idesc_fmt(uint32_t idesc_bf16, int tc_fmt) {
+  return tc_fmt == E4S_TC_F16 ? idesc_bf16 & ~((1u << 7) | (1u << 10)) : idesc_bf16;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // fused epilogue for one accumulator row (one output pixel) x 16 consecutive channels, shared by the tcgen05
 // kernels.  Per-channel vectors are read with 16-byte read-only loads (L1 resident), the pixel's 16 outputs leave
@@ -379,7 +412,14 @@ __device__ __forceinline__ void tc_epilogue16_sv(const E4SConv& p, const float (
 // 1.3e-5, and because the synthesis network is positively homogeneous the per-layer losses ADD UP along the 17 layers
 // into the dominant, coherent part of the end-to-end error.  The epilogues multiply the accumulator by this factor to
 // remove the mean of that bias (the random part of the truncation stays).
-__host__ __device__ __forceinline__ float tc_acc_unbias(int mma_steps) { return 1.f + 1.5e-8f * (float)mma_steps; }
+// fp16 operands (22-bit products) leave bits below the accumulator's ulp at almost every step, bf16 products (16 bits) only when they
+// are much smaller than the running sum: the per-step constant is per format (E4SConv.tc_unbias overrides it; < 0 disables).
+constexpr float TC_UNBIAS_BF16 = 1.5e-8f;
+constexpr float TC_UNBIAS_F16 = 1.7e-8f;       // 1.6e-8 (zero-mean operands) ... 2.5e-8 (same-signed sums), profiles/r2_acc_bias.txt
+__host__ __device__ __forceinline__ float tc_acc_unbias(const E4SConv& p, int mma_steps) {
+  const float per_step = p.tc_unbias != 0.f ? fmaxf(p.tc_unbias, 0.f) : (p.tc_fmt == E4S_TC_F16 ? TC_UNBIAS_F16 : TC_UNBIAS_BF16);
+  return (1.f + per_step * (float)mma_steps) * (p.tc_out_scale != 0.f ? p.tc_out_scale : 1.f);
+}
 
 // Fast epilogue (chosen once per kernel, outside every loop): no residual / float mask / accumulate / per-channel noise and an
 // activation of the piecewise-linear family.  sv = [mul | add | negative-side slope] per channel; NONE, ReLU, leaky ReLU

@@ -20,6 +20,7 @@ _ENGINE = os.environ.get("E4S_CONV_ENGINE", "tc")
 
 
 PROFILE = None        # set to a list by bench.py to time every conv launch with CUDA events
+TC_UNBIAS_OVERRIDE = None   # tests/micro/acc_bias.py: E4SConv.tc_unbias for every tensor-core launch (< 0 = no correction)
 
 
 def set_conv_engine(name: str):
@@ -47,6 +48,8 @@ class PackedConv:
     kw: int
     phases: int = 1
     tc: Optional[torch.Tensor] = None
+    tc_fmt: int = L.TC_BF16          # operand format of the tensor-core image (E4SConv.tc_fmt)
+    tc_out_scale: float = 1.0        # 1 / the power-of-two pre-scale of fp16 weights (E4SConv.tc_out_scale)
 
     @property
     def k(self) -> int:
@@ -88,25 +91,34 @@ def tc_available() -> bool:
     return int(L.lib().e4s_pack_weights_tc_bytes(1, 64, 32)) > 0
 
 
-def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, phases: int, want_tc: bool) -> PackedConv:
+def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, phases: int, want_tc: bool,
+                 tc_fmt: int = L.TC_BF16) -> PackedConv:
     cout_pad = pad_to(cout, 4)
     if cout_pad != cout:
         w_pkc = torch.nn.functional.pad(w_pkc, (0, cout_pad - cout))
     w_pkc = w_pkc.contiguous().float()
     pc = PackedConv(w_pkc, cin, cout, cout_pad, kh, kw, phases)
     if want_tc and w_pkc.is_cuda and tc_eligible(cin, cout) and tc_available():
-        pc.tc = L.pack_weights_tc(w_pkc, phases, pc.k, cin, cout, cout_pad)
+        scale = 1.0
+        if tc_fmt == L.TC_F16:
+            # fp16 operands: bring max|w| to [2^13, 2^14) with a power of two (exact), so that the lo parts of all but the
+            # tiniest weights stay normal fp16 numbers; the launch undoes it through E4SConv.tc_out_scale
+            mx = float(w_pkc.abs().max())
+            if mx > 0.0 and math.isfinite(mx):
+                scale = 2.0 ** (13 - math.floor(math.log2(mx)))
+        pc.tc = L.pack_weights_tc(w_pkc, phases, pc.k, cin, cout, cout_pad, tc_fmt, scale)
+        pc.tc_fmt, pc.tc_out_scale = tc_fmt, 1.0 / scale
     return pc
 
 
-def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, want_tc: bool = True) -> PackedConv:
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, want_tc: bool = True, tc_fmt: int = L.TC_BF16) -> PackedConv:
     """w [Co,Ci,kh,kw] -> k = (ky*kw + kx)*Ci_pad + ci rows, co contiguous."""
     co, ci, kh, kw = w.shape
     cin = ci if cin_pad is None else cin_pad
     t = w.detach().permute(2, 3, 1, 0)                      # [kh,kw,Ci,Co]
     if cin != ci:
         t = torch.nn.functional.pad(t, (0, 0, 0, cin - ci))
-    return _finish_pack(t.reshape(1, kh * kw * cin, co), cin, co, kh, kw, 1, want_tc)
+    return _finish_pack(t.reshape(1, kh * kw * cin, co), cin, co, kh, kw, 1, want_tc, tc_fmt)
 
 
 def pack_linear_weight(w: torch.Tensor, want_tc: bool = False) -> PackedConv:
@@ -249,6 +261,10 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     eng = engine or _ENGINE
     use_tc = eng == "tc" and pw.tc is not None
     use_rj = use_tc and region_jobs is not None and labels is not None
+    if use_tc:
+        p.tc_fmt, p.tc_out_scale = pw.tc_fmt, pw.tc_out_scale
+        if TC_UNBIAS_OVERRIDE is not None:
+            p.tc_unbias = TC_UNBIAS_OVERRIDE
 
     def launch():
         if use_rj and region_jobs.count is None:

@@ -31,15 +31,18 @@ def bn_affine(bn: nn.BatchNorm2d):
 
 
 import os
-# Default: the exact-fp32 CUDA-core engine (label maps differ from the CPU reference only where its own top-2 margin is
-# below fp32 reassociation noise).  "tc" (opt-in, E4S_BISENET_ENGINE=tc or set_bisenet_engine) runs the backbone on the
-# bf16x3 tensor-core engine: 4.7x faster (18.3 -> 3.9 ms per 16 faces), logits within 8e-5 relative, 15 of 1,048,576
-# argmax labels differ on the synthetic-weight test -- NOT the bit-exact bar, so it is never the default.
-_BISENET_ENGINE = [os.environ.get("E4S_BISENET_ENGINE", "f32")]
+# BiSeNet's label map has to match the reference's argmax, so its convolutions need fp32-class logits:
+#   "tc16" (default): tcgen05 with the fp16 hi/lo 3-pass split (operands exact to 2^-22, fp32 accumulate) -- the same
+#           kernels as the rest of the path, E4SConv.tc_fmt = E4S_TC_F16;
+#   "f32":  the exact-fp32 CUDA-core engine (4-5x slower; the cross-check of the tensor-core mode);
+#   "tc":   bf16 hi/lo split (2^-17 operands): logits within 8e-5 relative, 15 of 1,048,576 labels differ -- not the bar.
+# E4S_BISENET_ENGINE / set_bisenet_engine select the mode.
+_BISENET_ENGINE = [os.environ.get("E4S_BISENET_ENGINE", "tc16")]
+_TC_FMT = {"tc": L.TC_BF16, "tc16": L.TC_F16}
 
 
 def set_bisenet_engine(name: str):
-    if name not in ("f32", "tc"):
+    if name not in ("f32", "tc", "tc16"):
         raise ValueError(name)
     _BISENET_ENGINE[0] = name
 
@@ -48,13 +51,20 @@ def bisenet_engine() -> str:
     return _BISENET_ENGINE[0]
 
 
+def _conv_engine() -> str:
+    """engine.conv's engine name for the current mode."""
+    return "f32" if _BISENET_ENGINE[0] == "f32" else "tc"
+
+
 def packed(conv: nn.Conv2d, cin_pad=None, want_tc=False):
-    """Engine packing of a BiSeNet conv, cached per weight version (+ tensor-core image only in the opt-in tc mode)."""
-    want_tc = want_tc or _BISENET_ENGINE[0] == "tc"
-    key = _ver(conv.weight) + (want_tc,)
+    """Engine packing of a BiSeNet conv, cached per weight version and mode (tensor-core image in the tc modes)."""
+    mode = _BISENET_ENGINE[0]
+    want_tc = want_tc or mode != "f32"
+    key = _ver(conv.weight) + (want_tc, mode)
     c = getattr(conv, "_e4s_pack", None)
     if c is None or c[0] != key:
-        c = (key, E.pack_conv_weight(conv.weight.detach().float(), cin_pad=cin_pad, want_tc=want_tc))
+        c = (key, E.pack_conv_weight(conv.weight.detach().float(), cin_pad=cin_pad, want_tc=want_tc,
+                                     tc_fmt=_TC_FMT.get(mode, L.TC_BF16)))
         conv._e4s_pack = c
     return c[1]
 
@@ -63,7 +73,7 @@ def conv_bn(x: View, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool, res: View 
             cin_pad=None) -> View:
     scale, shift = bn_affine(bn)
     return E.conv(x, packed(conv, cin_pad), stride=conv.stride[0], pad=conv.padding[0], in_shift=in_shift, ch_scale=scale,
-                  ch_shift=shift, res=res, act=L.ACT_RELU if relu else L.ACT_NONE, out=out, engine=_BISENET_ENGINE[0])
+                  ch_shift=shift, res=res, act=L.ACT_RELU if relu else L.ACT_NONE, out=out, engine=_conv_engine())
 
 
 def conv3x3(in_planes, out_planes, stride=1):

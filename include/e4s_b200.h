@@ -48,6 +48,8 @@ extern "C" {
 /* activation codes for E4SConv.act */
 enum { E4S_ACT_NONE = 0, E4S_ACT_LRELU = 1, E4S_ACT_RELU = 2, E4S_ACT_PRELU = 3, E4S_ACT_SIGMOID = 4,
        E4S_ACT_RSQRT_EPS = 5 };
+/* E4SConv.tc_fmt */
+enum { E4S_TC_BF16 = 0, E4S_TC_F16 = 1 };
 /* E4SConv.mode */
 enum { E4S_CONV_NORMAL = 0, E4S_CONV_UP2_POLYPHASE = 1 };
 
@@ -105,6 +107,13 @@ typedef struct E4SConv {
    * otherwise every CTA exits at once.  Lets the host enqueue BOTH candidate kernels of a masked layer (per-(tile, region) jobs on the
    * halo kernel vs. the per-row gather / wide kernel) without reading the job count back: no host synchronisation inside a forward. */
   const int32_t* pred_count; int32_t pred_limit; int32_t pred_run_if_gt;
+  /* e4s_conv_tc only.  tc_fmt: operand format of the 3-pass split (must match the packed weights): E4S_TC_BF16 = two bf16 per value
+   * (2^-17 relative, any fp32 range: the StyleGAN2 / encoder layers), E4S_TC_F16 = two fp16 per value (2^-22 relative = fp32 class,
+   * activations must stay below 65504: BiSeNet, whose label map has to match the reference's argmax).  tc_out_scale multiplies the
+   * accumulator (0 = 1: undoes the power-of-two pre-scale e4s_pack_weights_tc_fmt applied to fp16 weights).  tc_unbias: relative
+   * correction per tcgen05.mma accumulate step for the truncating fp32 accumulate of the tensor core (0 = the library's measured
+   * default for the format, < 0 = none; tests/micro/acc_bias.py measures it). */
+  int32_t tc_fmt; float tc_out_scale; float tc_unbias;
 } E4SConv;
 
 const char* e4s_last_error(void);
@@ -140,6 +149,11 @@ int e4s_debug_halo_trace(void* buf, int cap_records);
 /* debug aid: profiling experiments on the halo kernel (bit0 skip epilogue math+stores, bit1 skip tcgen05.ld, bit2 skip MMAs); 0 = normal */
 int e4s_debug_halo_flags(int flags);
 int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, void* w_packed, void* stream);
+/* same with an explicit operand format (E4S_TC_*): every weight is multiplied by `scale` (a power of two chosen by the caller so that
+ * max|w|*scale ~ 2^14: keeps the fp16 lo parts out of the subnormal range) before the hi/lo split; the launch passes 1/scale as
+ * E4SConv.tc_out_scale.  fmt = E4S_TC_BF16, scale = 1 is e4s_pack_weights_tc. */
+int e4s_pack_weights_tc_fmt(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, int fmt, float scale, void* w_packed,
+                            void* stream);
 
 /* upfirdn2d on NCHW fp32 [planes, in_h, in_w] (planes = B*C). kernel [kh,kw] is correlated FLIPPED. */
 int e4s_upfirdn2d_f32(const float* x, const float* kernel, float* out, int64_t planes, int in_h, int in_w,
@@ -231,6 +245,12 @@ int e4s_swap_comp_styles_f32(const float* target, const float* source, float* ou
 /* tensor2im on the device (reference utils/torch_utils.py:64-76), batched: x NCHW [batch,3,h,w] fp32 -> y NHWC [batch,h,w,3] u8:
  * (v+1)/2 when zero_center, clamp [0,1], *255, truncate (the reference's float32 numpy arithmetic: identical bytes) */
 int e4s_tensor2im_u8(const float* x, uint8_t* y, int batch, int h, int w, int zero_center, void* stream);
+
+/* TO_TENSOR (+ NORMALIZE) on the device (reference datasets/dataset.py:45 and its callers face_swap_video_pipeline.py:338-346,
+ * face_parsing_demo.py:153), batched: x u8 HWC [batch,h,w,3] -> y01 = v/255 and / or ynorm = (v/255 - mean[c]) / std[c], both fp32 NCHW
+ * [batch,3,h,w] (either may be NULL).  mean3 / std3 are HOST arrays of 3 floats.  Same fp32 operations as torchvision: identical floats. */
+int e4s_im2tensor_f32(const uint8_t* x, float* y01, float* ynorm, int batch, int h, int w, const float* mean3, const float* std3,
+                      void* stream);
 
 /* Grey-scale dilation / erosion of NCHW planes (reference utils/morphology.py:23-200): x, out [planes, h, w] fp32; neighborhood
  * [se_h, se_w] = 0 (or the non-flat structuring element) where the kernel is non-zero and -max_val elsewhere; out-of-image taps

@@ -136,7 +136,7 @@ def conv_batched(params_list):
         conv(p)
 
 
-def pack_weights_tc(w, phases, k, cin, cout, cout_pad):
+def pack_weights_tc(w, phases, k, cin, cout, cout_pad, fmt=0, scale=1.0):
     return None
 
 

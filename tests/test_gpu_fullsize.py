@@ -125,15 +125,19 @@ def test_net3_1024_vs_oracle():
     assert torch.equal(solo[0], out[1])
 
 
-def test_bisenet_512_argmax_vs_oracle():
-    """BASELINE config 4 shape at B=4: argmax label maps vs the oracle; mismatches only where the oracle's own
-    top-2 margin is within fp32 reassociation noise of a tie."""
+def _bisenet_vs_oracle(engine, batch=4):
+    from e4s2024_b200.face_parsing import resnet as rn
     from e4s2024_b200.face_parsing.model import BiSeNet
     seg = BiSeNet(19)
     sd = synth.synth_module_weights(seg, seed=10)
     seg = seg.cuda().eval()
-    x = synth.randn("bise512.x", (4, 3, 512, 512), 14)
-    o, o16, o32 = seg(x.cuda())
+    x = synth.randn("bise512.x", (batch, 3, 512, 512), 14)
+    prev = rn.bisenet_engine()
+    rn.set_bisenet_engine(engine)
+    try:
+        o, o16, o32 = seg(x.cuda())
+    finally:
+        rn.set_bisenet_engine(prev)
     ref = orc.bisenet_forward({k: v.cpu() for k, v in sd.items()}, x)[0]
     scale = float(ref.abs().max())
     d = float((o.cpu() - ref).abs().max())
@@ -142,10 +146,26 @@ def test_bisenet_512_argmax_vs_oracle():
     top2 = torch.topk(ref, 2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1])
     worst = float(margin[bad].max()) if bad.any() else 0.0
-    print(f"BiSeNet 512^2 B=4: logits max|diff| {d:.3e} (scale {scale:.1f}); label mismatches {int(bad.sum())} of {bad.numel()}, "
-          f"largest oracle margin at a mismatch {worst:.3e}")
+    print(f"BiSeNet 512^2 B={batch} engine {engine}: logits max|diff| {d:.3e} (scale {scale:.1f}); label mismatches {int(bad.sum())} of "
+          f"{bad.numel()}, largest oracle margin at a mismatch {worst:.3e}")
+    return d, scale, int(bad.sum()), worst
+
+
+@pytest.mark.parametrize("engine", ["tc16", "f32"])
+def test_bisenet_512_argmax_vs_oracle(engine):
+    """BASELINE config 4 shape at B=4: argmax label maps vs the oracle; mismatches only where the oracle's own top-2 margin is
+    within fp32 reassociation noise of a tie.  The SAME bar for the default tensor-core mode (tcgen05, fp16 hi/lo split) and for
+    the exact-fp32 CUDA-core engine that cross-checks it."""
+    d, scale, nbad, worst = _bisenet_vs_oracle(engine)
     assert d < 3e-5 * scale
-    assert int(bad.sum()) <= 16 and worst < 2e-5 * scale
+    assert nbad <= 16 and worst < 2e-5 * scale
+
+
+def test_bisenet_bf16_split_is_not_enough():
+    """Why BiSeNet does not share the generator's bf16 hi/lo format: its logits are 2-3x further from the oracle and label flips
+    appear at margins fp32 arithmetic resolves.  (Documents the choice; only a loose bound is asserted.)"""
+    d, scale, nbad, worst = _bisenet_vs_oracle("tc")
+    assert d < 3e-4 * scale and nbad < 200
 
 
 def test_fused_torgb_matches_separate_torgb(monkeypatch):
