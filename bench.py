@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- 1024^2 faces/sec of the E4S hot path on N B200s (BASELINE.json metric).
+"""bench.py -- 1024^2 faces/sec of the E4S swap hot path on N B200s (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[1] -- batch=16 per GPU, 1024x1024 StyleGAN2 regional
-synthesis (Generator(1024, rl=13, split=5), K=12 regions) from random regional style codes, blocky one-hot
-masks, fixed noise buffers, synthetic weights.  A "step" = one Generator.forward over the batch.
+Workload (config.workload): the per-GPU shard of BASELINE.json configs[4] -- 16 faces per GPU through the FULL path
+    uint8 1024^2 image -> TO_TENSOR/NORMALIZE -> bicubic 1024->512 + BiSeNet + argmax + seg19->12 LUT -> one-hot
+    -> Net3 (regional style encoder, 12 LocalMLPs, mask-guided StyleGAN2 1024^2, K=12, rl=13) -> tensor2im (uint8)
+    [-> NCCL all-gather of the uint8 images + label maps when N > 1]
+through `e4s2024_b200.sharding.SwapHotPath` (the public entry), synthetic weights and FFHQ-shaped synthetic images.
+A "step" = one pass of that path over the 16-face shard of every rank.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # this framework (CUDA, libe4s_b200.so)
   python bench.py --impl reference ...                         # the reference algorithm on the host CPU cores
 
-value  : whole-job faces/s with inputs resident in HBM (CUDA events, max over ranks).
-e2e    : same metric through the public nn.Module API with HOST (pinned) latent+mask copied in and the
-         images copied back to pinned host memory inside the timed region.
-roofline / cpu_baseline: see DESIGN.md "Measurement".
+value    : whole-job faces/s, inputs (uint8 images) resident in HBM, CUDA events, max over ranks, gathers inside the timed region.
+e2e      : same metric with HOST buffers: pinned uint8 images in, uint8 images + u8 label maps out, every step, through
+           serving.HostPipeline (double-buffered copies), timed from the first H2D to the last D2H.
+roofline : the convolution launches of one step (the tcgen05 kernels that carry 405.5 GFLOP/face), per stage.
+Extra keys (N = 1): configs[1] generator-only (three mask families), configs[2] (B=32 Net3), configs[3] (B=64 BiSeNet),
+           gpu_reference (the reference algorithm as torch/cuDNN ops on the same B200, TF32 off / on), parity, cpu_baseline.
+See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -22,15 +28,19 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "1024^2 faces/sec (StyleGAN2 regional synthesis, Generator 1024 K=12 rl=13)"
+METRIC = "1024^2 faces/sec (StyleGAN2 synthesis+encoder+parsing: full swap hot path)"
 BATCH, SIZE, K, RL, SPLIT = 16, 1024, 12, 13, 5
-ALG_GFLOP_PER_FACE = 148.52          # SURVEY.md section 8(d) per-layer table (each output pixel once)
+# algorithmic GFLOP per face (each output pixel once, conv_transpose at input resolution)
+ALG_GFLOP = {"parse": 27.54, "encoder": 229.34, "mlps": 0.10, "generator": 148.52}
+ALG_GFLOP_PER_FACE = 405.5
+LABEL_TIE_RULE = "labels may differ from the CPU oracle only where the oracle's own top-2 logit margin is < 2e-5 x max|logit| (fp32 reassociation noise)"
 
 
 def peaks():
@@ -38,7 +48,7 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "hbm_gbs": d["hbm_gbs"],
-                "source": "MEASURED_PEAKS.json (sustained bf16, copy bandwidth)"}
+                "source": "MEASURED_PEAKS.json (sustained bf16 cuBLAS rate: the kernels are timed inside a long step; copy bandwidth)"}
     return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback"}
 
 
@@ -74,82 +84,38 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def net3_opts():
+    # the fields Net3 reads from the reference's option object (options/our_swap_face_pipeline_options.py:12-18,50)
+    return types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=RL, num_seg_cls=K, out_size=SIZE, train_G=False,
+                                 start_from_latent_avg=True, learn_in_w=False)
+
+
 def bench_config(world, engine="tc"):
     """`config` of the JSON line: the same dict for both arms (the reference arm adds what its bounded sample was)."""
-    return {"workload": "configs[1]: batch=16/GPU 1024x1024 StyleGAN2 regional synthesis from random regional style codes",
+    return {"workload": "configs[4] per-GPU shard (the configuration the metric is quoted on): 16 faces/GPU, full swap hot path "
+                        "(bicubic 1024->512 + BiSeNet + argmax/LUT -> one-hot -> Net3: encoder, 12 LocalMLPs, StyleGAN2 1024^2 K=12 rl=13)",
             "batch_per_gpu": BATCH, "global_batch": BATCH * world, "size": SIZE, "regions": K, "remaining_layer_idx": RL,
-            "masks": "blocky one-hot 32x32 cells @512^2", "noise": "registered buffers (randomize_noise=False)",
-            "parallelism": f"batch-sharded x{world}" + (" + NCCL all_gather of images" if world > 1 else ""),
-            "conv_engine": engine, "l2": "working set (>2 GB activations per step) exceeds the 126 MB L2"}
+            "inputs": "uint8 HWC 1024^2 images (low-pass noise, FFHQ-shaped); masks come from the parser on those images",
+            "noise": "registered buffers (randomize_noise=False)",
+            "parallelism": f"batch-sharded x{world}" + (" + NCCL all_gather of the uint8 images and label maps (async, double-buffered)" if world > 1 else ""),
+            "conv_engine": engine, "label_tie_rule": LABEL_TIE_RULE,
+            "l2": "working set (>2 GB of activations per step) exceeds the 126 MB L2; no flush needed"}
 
 
-def swap_path_line(dev, steps=3):
-    """BASELINE.json's metric names the whole swap hot path (parsing + encoder + synthesis, configs[4] per GPU shard):
-    FaceParser.parse_batch -> one-hot -> Net3.forward at 16 faces, inputs resident, CUDA events, stage by stage."""
-    from e4s2024_b200 import _lib as L, synth
+def build_path(dev, seed_net=9, seed_seg=10):
+    from e4s2024_b200 import synth
     from e4s2024_b200.face_parsing.face_parsing_demo import FaceParser
     from e4s2024_b200.networks import Net3
-    import types
-    # the fields Net3 reads from the reference's option object (options/our_swap_face_pipeline_options.py:12-18,50)
-    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=RL, num_seg_cls=K, out_size=SIZE, train_G=False,
-                                 start_from_latent_avg=True, learn_in_w=False)
-    net = Net3(opts)
-    synth.synth_module_weights(net, seed=9)
+    from e4s2024_b200.sharding import SwapHotPath
+    net = Net3(net3_opts())
+    sd_net = synth.synth_module_weights(net, seed=seed_net)
     net = net.to(dev)
-    net.latent_avg = synth.randn("net3.latent_avg", (18, 512), 9, 0.1).to(dev)
+    la = synth.randn("net3.latent_avg", (18, 512), seed_net, 0.1)
+    net.latent_avg = la.to(dev)
     parser = FaceParser(seg_ckpt=None, size=SIZE, device=str(dev))
-    synth.synth_module_weights(parser.seg, seed=10)
+    sd_seg = synth.synth_module_weights(parser.seg, seed=seed_seg)
     parser.seg.to(dev)
-    img = synth.smooth_image("swap.img", BATCH, SIZE, 13).to(dev)
-    img01 = (img + 1) / 2
-
-    def t(fn):
-        r = fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            r = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps, r
-
-    ms_parse, lab = t(lambda: parser.parse_batch(img01))
-    ms_onehot, mask = t(lambda: L.labels_to_onehot(lab, K))
-    ms_enc, (vec, _) = t(lambda: net.get_style_vectors(img, mask))
-    ms_codes, codes = t(lambda: net.cal_style_codes(vec))
-    ms_gen, _ = t(lambda: net.gen_img(None, codes, mask, randomize_noise=False))
-    ms_all, _ = t(lambda: net(img, L.labels_to_onehot(parser.parse_batch(img01), K), randomize_noise=False))
-    # opt-in fast parse (bf16x3 tensor-core BiSeNet): reported beside the exact mode, never instead of it
-    from e4s2024_b200.face_parsing import resnet as _rn
-    _rn.set_bisenet_engine("tc")
-    ms_parse_tc, lab_tc = t(lambda: parser.parse_batch(img01))
-    ms_all_tc, _ = t(lambda: net(img, L.labels_to_onehot(parser.parse_batch(img01), K), randomize_noise=False))
-    _rn.set_bisenet_engine("f32")
-    differing = int((lab_tc != lab).sum())
-    del net, parser
-    return {"workload": "configs[4] per-GPU shard: 16 faces, bicubic 1024->512 + BiSeNet + argmax/LUT -> one-hot -> Net3 (encoder, 12 MLPs, generator)",
-            "value": BATCH / ms_all * 1e3, "unit": "faces/s", "ms_per_step": ms_all,
-            "stage_ms": {"parse": ms_parse, "onehot": ms_onehot, "encoder": ms_enc, "mlps": ms_codes, "generator": ms_gen},
-            "alg_gflop_per_face": 405.5, "note": "BiSeNet runs on the exact-fp32 CUDA-core engine (bit-exact label maps), the rest on tcgen05",
-            "fast_parse_opt_in": {"value": BATCH / ms_all_tc * 1e3, "unit": "faces/s", "ms_per_step": ms_all_tc, "parse_ms": ms_parse_tc,
-                                  "labels_differing_from_exact_mode": differing, "labels_total": int(lab.numel()),
-                                  "note": "E4S_BISENET_ENGINE=tc: BiSeNet on the bf16x3 tensor-core engine; does not meet the bit-exact label bar, not the default"}}
-
-
-def make_generator_inputs(batch, seed=1):
-    from e4s2024_b200 import synth
-    latent = synth.randn("bench.latent", (batch, K, 18, 512), seed)
-    labels = synth.blocky_labels(batch, K, 512, cells=32, seed=seed)
-    return latent, synth.onehot(labels, K)
-
-
-def build_generator(device):
-    from e4s2024_b200 import synth
-    from e4s2024_b200.stylegan2.model import Generator
-    G = Generator(SIZE, 512, 8, split_layer_idx=SPLIT, remaining_layer_idx=RL)
-    synth.synth_module_weights(G, seed=2)
-    return G.to(device).eval()
+    return SwapHotPath(net, parser, K), {"net": sd_net, "seg": sd_seg, "latent_avg": la}
 
 
 def thread_candidates():
@@ -159,41 +125,82 @@ def thread_candidates():
     return sorted({n, min(n, 64), min(n, 32), min(n, 16)}, reverse=True)
 
 
-def cpu_baseline(faces=1):
-    """The oracle (CPU restatement of the reference algorithm: K=12 grouped convs per masked layer) on the host cores."""
-    from e4s2024_b200 import synth
-    from e4s2024_b200.stylegan2.model import generator_state_shapes
+def oracle_chain(sds, img_u8, labels_override=None):
+    """The reference algorithm for one batch on whatever device the tensors live on (oracle/e4s_oracle.py): TO_TENSOR / NORMALIZE,
+    face_parse (bicubic + BiSeNet + argmax + LUT), labelMap2OneHot, Net3.forward (encoder, MLPs, K grouped convs per masked layer),
+    tensor2im.  -> (image fp32 [B,3,S,S], labels u8 [B,512,512] numpy, logits-free)."""
     from oracle import e4s_oracle as orc
-    sd = synth.fill_state_dict(generator_state_shapes(SIZE, split_layer_idx=SPLIT, remaining_layer_idx=RL), seed=2)
-    latent, mask = make_generator_inputs(faces)
-    best, best_t, tried = None, None, {}
+    x01 = img_u8.permute(0, 3, 1, 2).float().div(255)
+    x = (x01 - 0.5) / 0.5
+    labels = orc.face_parse(sds["seg"], x01)
+    lab_t = torch.from_numpy(labels if labels_override is None else labels_override).to(x.device).long()[:, None]
+    mask = orc.label_to_onehot(lab_t, K)
+    image = orc.net3_forward(sds["net"], x, mask, sds["latent_avg"], out_size=SIZE, remaining_layer_idx=RL)[0]
+    return image, labels
+
+
+def cpu_state(sds):
+    return {"net": {k: v.cpu() for k, v in sds["net"].items()}, "seg": {k: v.cpu() for k, v in sds["seg"].items()},
+            "latent_avg": sds["latent_avg"].cpu()}
+
+
+def cpu_baseline(sds, img_u8_1, gpu_labels_1=None):
+    """The oracle (CPU restatement of the reference algorithm) for ONE face of the workload on the host cores; also returns its
+    outputs so the same run reports parity of the GPU path against it."""
+    sd = cpu_state(sds)
+    best, best_t, tried, out = None, None, {}, None
     with torch.no_grad():
         for t in thread_candidates():
             torch.set_num_threads(t)
             t0 = time.perf_counter()
-            orc.generator_forward(sd, SIZE, latent, mask, split_layer_idx=SPLIT, remaining_layer_idx=RL)
+            out = oracle_chain(sd, img_u8_1)
             dt = time.perf_counter() - t0
             tried[t] = round(dt, 2)
             if best is None or dt < best:
                 best, best_t = dt, t
-            if dt > 45:                       # keep the whole bench within minutes
-                continue
-    return {"value": faces / best, "unit": "faces/s", "cores": best_t, "kind": "port",
-            "sample": f"{faces} face, Generator 1024^2 K=12 rl=13, oracle/e4s_oracle.py fp32; seconds per thread count {tried}"}
+        image, labels = out
+        if gpu_labels_1 is not None and (labels != gpu_labels_1).any():
+            # image parity is judged on the same mask: re-run the oracle's Net3 on the GPU path's label map (the label map itself
+            # is compared separately, under the tie rule)
+            torch.set_num_threads(best_t)
+            image, _ = oracle_chain(sd, img_u8_1, labels_override=gpu_labels_1)
+    return ({"value": 1.0 / best, "unit": "faces/s", "cores": best_t, "kind": "port",
+             "sample": f"1 face of the workload through the full path (parse + one-hot + Net3), oracle/e4s_oracle.py fp32; seconds per thread count {tried}"},
+            image, labels)
+
+
+def label_parity(sds, img_u8_1, gpu_labels_1):
+    """Flip count and the oracle's top-2 margin at the flips for one face."""
+    from oracle import e4s_oracle as orc
+    sd = {k: v.cpu() for k, v in sds["seg"].items()}
+    with torch.no_grad():
+        x01 = img_u8_1.permute(0, 3, 1, 2).float().div(255)
+        logits = orc.bisenet_forward(sd, orc.parser_preprocess(x01, SIZE))[0]
+    lab19 = logits.argmax(1)
+    ref12 = torch.from_numpy(orc.SEG19_TO_SEG12)[lab19.long()]
+    bad = ref12 != torch.from_numpy(gpu_labels_1).to(ref12.dtype)
+    top2 = torch.topk(logits, 2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    scale = float(logits.abs().max())
+    return {"labels_compared": int(bad.numel()), "label_flips_vs_cpu_oracle": int(bad.sum()),
+            "max_oracle_margin_at_a_flip": float(margin[bad].max()) if bad.any() else 0.0,
+            "tie_threshold": 2e-5 * scale, "logit_absmax": scale, "tie_rule": LABEL_TIE_RULE}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = bench_config(max(int(os.environ.get("WORLD_SIZE", "1")), 1), engine="cpu")
-    cfg["sample"] = "1 face per step (bounded sample of the 16-face batch), CPU reference algorithm, all host threads that help"
     from e4s2024_b200 import synth
-    from e4s2024_b200.stylegan2.model import generator_state_shapes
-    from oracle import e4s_oracle as orc
-    sd = synth.fill_state_dict(generator_state_shapes(SIZE, split_layer_idx=SPLIT, remaining_layer_idx=RL), seed=2)
-    latent, mask = make_generator_inputs(1)
-    step = lambda: orc.generator_forward(sd, SIZE, latent, mask, split_layer_idx=SPLIT, remaining_layer_idx=RL)
+    from e4s2024_b200.face_parsing.model import bisenet_state_shapes
+    from e4s2024_b200.networks import net3_state_shapes
+    cfg = bench_config(max(int(os.environ.get("WORLD_SIZE", "1")), 1), engine="cpu")
+    cfg["sample"] = ("1 face per step (bounded sample of the 16-face shard) through the full path, CPU reference algorithm; the warm-up "
+                     "steps double as a search over host thread counts (oneDNN does not scale to every hardware thread)")
+    sd = {"net": synth.fill_state_dict(net3_state_shapes(net3_opts()), seed=9), "seg": synth.fill_state_dict(bisenet_state_shapes(19), seed=10),
+          "latent_avg": synth.randn("net3.latent_avg", (18, 512), 9, 0.1)}
+    img = synth.smooth_image_u8("swap.img", 1, SIZE, 13)
+    step = lambda: oracle_chain(sd, img)
     cands = thread_candidates()
     threads, best = cands[0], None
     with torch.no_grad():
@@ -216,8 +223,152 @@ def run_reference(args):
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": cfg, "gpu_launches": 0,
                       "cpu_baseline": {"value": v, "unit": "faces/s", "cores": threads, "kind": "port",
-                                       "sample": "1 face per step, oracle/e4s_oracle.py generator_forward"},
+                                       "sample": "1 face per step, oracle/e4s_oracle.py: face_parse + one-hot + net3_forward"},
                       "e2e": {"value": v, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def time_steps(fn, steps, warmup=2):
+    """ms per call of fn (CUDA events on the current stream, synchronised on both sides)."""
+    r = None
+    for _ in range(warmup):
+        r = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, r
+
+
+def stage_breakdown(hot, img_u8_d, steps=5):
+    """The stages of one step, each timed alone (CUDA events), plus the per-launch pass for the roofline."""
+    from e4s2024_b200 import _lib as L
+    from e4s2024_b200 import engine as E
+    net, parser = hot.net, hot.parser
+    ms = {}
+    ms["im2tensor"], (img01, img) = time_steps(lambda: L.im2tensor(img_u8_d), steps)
+    ms["parse"], lab = time_steps(lambda: parser.parse_batch(img01), steps)
+    ms["onehot"], mask = time_steps(lambda: L.labels_to_onehot(lab, K), steps)
+    ms["encoder"], (vec, _) = time_steps(lambda: net.get_style_vectors(img, mask), steps)
+    ms["mlps"], codes = time_steps(lambda: net.cal_style_codes(vec), steps)
+    ms["generator"], (out, _, _) = time_steps(lambda: net.gen_img(None, codes, mask, randomize_noise=False), steps)
+    ms["tensor2im"], _ = time_steps(lambda: L.tensor2im_u8(out, True), steps)
+    # per-launch pass: CUDA events around every convolution launch (engine.conv), tagged with its stage
+    E.PROFILE = []
+    for stage, fn in (("parse", lambda: parser.parse_batch(img01)), ("encoder", lambda: net.get_style_vectors(img, mask)),
+                      ("generator", lambda: net.gen_img(None, codes, mask, randomize_noise=False))):
+        E.PROFILE_STAGE = stage
+        fn()
+    torch.cuda.synchronize()
+    prof, E.PROFILE, E.PROFILE_STAGE = E.PROFILE, None, None
+    ctx = E.RegionCtx(mask, net.G._region_job_keys(), lazy=False)          # how the parser's masks tile: region jobs per 16x8 tile
+    ms["mask_region_jobs_per_tile"] = {f"{h}x{w}{'_up' if up else ''}": round(rj.count / max(rj.tiles, 1), 3) for (h, w, up), rj in ctx.region_jobs.items()}
+    return ms, prof
+
+
+def roofline_from(prof, batch, step_ms, traffic):
+    pk = peaks()
+    by = {}
+    for r in prof:
+        d = by.setdefault(r["stage"], {"ms": 0.0, "alg": 0.0, "exec": 0.0, "n": 0})
+        d["ms"] += r["ev"][0].elapsed_time(r["ev"][1])
+        d["alg"] += r["alg_flops"]
+        d["exec"] += r["exec_flops"]
+        d["n"] += 1
+    conv_ms = sum(d["ms"] for d in by.values())
+    if conv_ms <= 0:
+        return None
+    alg = ALG_GFLOP_PER_FACE * 1e9 * batch                     # SURVEY 8(d) per-face figure x faces per step
+    counted = sum(d["alg"] for d in by.values())
+    ach = alg / (conv_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_tc_{halo,wide,gather} (tcgen05, 3-pass hi/lo split: bf16 in the encoder / generator, fp16 in BiSeNet): "
+                                         "every convolution launch of one step",
+            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic,
+            "peak_source": pk["source"], "launches": sum(d["n"] for d in by.values()), "kernel_ms_per_step": conv_ms,
+            "conv_share_of_step": conv_ms / step_ms if step_ms else None,
+            "alg_gflop_per_face": ALG_GFLOP_PER_FACE, "alg_gflop_per_face_counted_from_launches": counted / batch / 1e9,
+            "executed_tflops": sum(d["exec"] for d in by.values()) / (conv_ms * 1e-3) / 1e12,
+            "by_stage": {k: {"ms": v["ms"], "launches": v["n"], "alg_tflops": v["alg"] / (v["ms"] * 1e-3) / 1e12,
+                             "frac_of_peak": v["alg"] / (v["ms"] * 1e-3) / 1e12 / pk["bf16_tflops"],
+                             "frac_of_3pass_peak": 3 * v["alg"] / (v["ms"] * 1e-3) / 1e12 / pk["bf16_tflops"]} for k, v in by.items()},
+            "note": "achieved = 405.5 GFLOP/face (SURVEY 8d: each output pixel once, conv_transpose at input resolution) x 16 faces / summed "
+                    "CUDA-event durations of the convolution launches of one step; the 3-pass split issues 3 MMAs per product (so 1/3 of the "
+                    "peak is the ceiling of this arithmetic: frac_of_3pass_peak) and the poly-phase up-convs execute 4x their algorithmic MACs "
+                    "(executed_tflops counts those, not the split)"}
+
+
+def generator_only(dev, steps):
+    """BASELINE.json configs[1] (batch=16 synthesis from random regional style codes) for three mask families."""
+    from e4s2024_b200 import engine as E
+    from e4s2024_b200 import synth
+    from e4s2024_b200.stylegan2.model import Generator
+    G = Generator(SIZE, 512, 8, split_layer_idx=SPLIT, remaining_layer_idx=RL)
+    synth.synth_module_weights(G, seed=2)
+    G = G.to(dev).eval().requires_grad_(False)
+    latent = synth.randn("bench.latent", (BATCH, K, 18, 512), 1).to(dev)
+    out = {"workload": "configs[1]: batch=16 1024x1024 StyleGAN2 regional synthesis from random regional style codes, inputs resident",
+           "alg_gflop_per_face": ALG_GFLOP["generator"], "masks": {}}
+    for kind in ("blocky", "face", "noise"):
+        mask = synth.onehot(synth.make_labels(kind, BATCH, K, 512, seed=1), K).to(dev)
+        ms, _ = time_steps(lambda: G([latent], None, mask, input_is_latent=True, randomize_noise=False), steps, warmup=3)
+        ctx = E.RegionCtx(mask, G._region_job_keys(), lazy=False)        # synchronous context: job counts for the report
+        jobs = {f"{h}x{w}{'_up' if up else ''}": round(rj.count / max(rj.tiles, 1), 3) for (h, w, up), rj in ctx.region_jobs.items()}
+        out["masks"][kind] = {"value": BATCH / ms * 1e3, "unit": "faces/s", "ms_per_step": ms, "region_jobs_per_tile": jobs,
+                              "alg_tflops": BATCH / ms * ALG_GFLOP["generator"]}
+    out["mask_kinds"] = {"blocky": "random class per 32x32 cell of the 512^2 label map (tile-aligned at every resolution >= 64^2)",
+                         "face": "procedural face (ellipses, curved boundaries; regions per 16x8 tile 1.4 / 1.8 / 2.7 / 4.9 at 256^2 / 128^2 / 64^2 / 32^2, "
+                                 "the statistics of the reference's bundled CelebA-HQ masks, SURVEY B.6)",
+                         "noise": "independent random class per pixel (adversarial: every tile sees all 12 regions)"}
+    del G
+    return out
+
+
+def other_configs(hot, dev, steps=3):
+    """configs[2] (batch=32 encoder -> regional styles -> synthesis round trip) and configs[3] (BiSeNet batch=64 at 512^2)."""
+    from e4s2024_b200 import _lib as L
+    from e4s2024_b200 import synth
+    res = {}
+    img = synth.smooth_image("cfg2.img", 32, SIZE, 17).to(dev)
+    mask = synth.onehot(synth.make_labels("blocky", 32, K, 512, seed=17), K).to(dev)
+    ms, _ = time_steps(lambda: hot.net(img, mask, randomize_noise=False), steps, warmup=2)
+    res["net3_b32"] = {"workload": "configs[2]: batch=32 Net3.forward (encoder -> regional styles -> synthesis), blocky masks, inputs resident",
+                       "value": 32 / ms * 1e3, "unit": "faces/s", "ms_per_step": ms,
+                       "alg_tflops": 32 / ms * (ALG_GFLOP["encoder"] + ALG_GFLOP["mlps"] + ALG_GFLOP["generator"])}
+    del img, mask
+    torch.cuda.empty_cache()
+    x = synth.randn("cfg3.x", (64, 512, 512, 8), 18)
+    x[..., 3:] = 0
+    x = x.to(dev)
+    ms, _ = time_steps(lambda: hot.parser.seg.labels(x, (512, 512), None), steps, warmup=2)
+    res["bisenet_b64"] = {"workload": "configs[3]: BiSeNet forward batch=64 512x512 -> 19-class label map (x8 upsample + argmax fused), inputs resident",
+                          "value": 64 / ms * 1e3, "unit": "faces/s", "ms_per_step": ms, "alg_tflops": 64 / ms * ALG_GFLOP["parse"]}
+    return res
+
+
+def gpu_reference(sds, img_u8_d, batch=8, reps=2):
+    """The 'existing Blackwell path' (BASELINE.md section 4.5): the reference ALGORITHM as plain torch ops on the same
+    B200 -- K = 12 grouped cuDNN convolutions + mask multiply-adds per masked layer, materialised per-sample weights, separate
+    blur / bias-act passes -- with TF32 off (fp32 parity mode) and on (cuDNN's default)."""
+    dev = img_u8_d.device
+    sd = {"net": {k: v.to(dev) for k, v in sds["net"].items()}, "seg": {k: v.to(dev) for k, v in sds["seg"].items()},
+          "latent_avg": sds["latent_avg"].to(dev)}
+    x = img_u8_d[:batch]
+    out = {"workload": f"full path, batch={batch}, oracle/e4s_oracle.py ops on cuda (cuDNN {torch.backends.cudnn.version()}), inputs resident"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                ms, _ = time_steps(lambda: oracle_chain(sd, x), reps, warmup=1)
+            out[tag] = {"value": batch / ms * 1e3, "unit": "faces/s", "ms_per_step": ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    del sd
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -228,9 +379,7 @@ def main():
     ap.add_argument("--impl", default="e4s_b200", choices=["e4s_b200", "reference"])
     ap.add_argument("--engine", default=None, choices=[None, "tc", "f32"], help="conv engine override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-swap-path", action="store_true", help="skip the full swap-path (parser + encoder + generator) timing")
-    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per forward (serving.GraphedGenerator) instead of launching "
-                    "every kernel from the host; measured equal on one B200 (the step is GPU-bound), so the eager path stays the default")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs[1..3], gpu_reference and the stage / roofline pass")
     ap.add_argument("--dump-layers", default=None, help="write per-conv-launch timings (JSON lines) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -239,6 +388,9 @@ def main():
     import torch.distributed as dist
     from e4s2024_b200 import _lib as L
     from e4s2024_b200 import engine as E
+    from e4s2024_b200 import synth
+    from e4s2024_b200.serving import HostPipeline
+    from e4s2024_b200.sharding import AsyncGather
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,66 +404,24 @@ def main():
         E.set_conv_engine(args.engine)
     args.warmup = max(args.warmup, 3)
 
-    G = build_generator(dev)
-    latent_h, mask_h = make_generator_inputs(BATCH, seed=1 + rank)
-    latent_h, mask_h = latent_h.pin_memory(), mask_h.pin_memory()
-    latent_d, mask_d = latent_h.to(dev), mask_h.to(dev)
-    # the path's only exchange: all-gather of the output images, double-buffered and asynchronous so that the gather of
-    # step i rides under the kernels of step i+1 (NVLink/NVSwitch traffic, no dependence on the next step's inputs)
-    gathered = [torch.empty(world * BATCH, 3, SIZE, SIZE, device=dev) for _ in range(2)] if world > 1 else None
-    inflight = []
-    out_h = torch.empty(BATCH, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory()     # what tensor2im hands the host: uint8 HWC images
-
-    # One CUDA graph per forward (serving.GraphedGenerator): the ~40 launches of a step replay as one; the eager path stays for
-    # the per-launch timing pass and --no-graph.
-    from e4s2024_b200.serving import GraphedGenerator
-    G([latent_d], None, mask_d, input_is_latent=True, randomize_noise=False)          # first forward also packs the weights
-    n0 = L.launch_count()
-    G([latent_d], None, mask_d, input_is_latent=True, randomize_noise=False)
-    launches_per_forward = L.launch_count() - n0
-    gg = None if not args.graph else GraphedGenerator(G, BATCH, K, (mask_d.shape[2], mask_d.shape[3]), device=dev)
-
-    def gen(lat, msk):
-        if gg is None:
-            return G([lat], None, msk, input_is_latent=True, randomize_noise=False)[0]
-        return gg(lat, msk)
+    hot, sds = build_path(dev)
+    img_h = synth.smooth_image_u8("swap.img", BATCH, SIZE, 13 + rank).pin_memory()        # what a pipeline holds: uint8 HWC
+    img_d = img_h.to(dev)
+    out_h = (torch.empty(BATCH, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory(), torch.empty(BATCH, 512, 512, dtype=torch.uint8).pin_memory())
+    # the path's only exchange: all-gather of the uint8 images + label maps, asynchronous and double-buffered
+    gather = AsyncGather(world, [((BATCH, SIZE, SIZE, 3), torch.uint8), ((BATCH, 512, 512), torch.uint8)], dev) if world > 1 else None
 
     def step_resident():
-        img = gen(latent_d, mask_d)
-        if world > 1 and gg is not None:
-            img = img.clone()                            # the graph's static output is overwritten by the next replay
-        if world > 1:
-            if len(inflight) == 2:                       # the buffer about to be reused: its gather must have completed
-                inflight.pop(0).wait()
-            buf = gathered[step_resident.n % 2]
-            step_resident.n += 1
-            inflight.append(dist.all_gather_into_tensor(buf, img, async_op=True))
-        return img
+        out_u8, labels = hot.run_shard_u8(img_d)
+        if gather is not None:
+            gather.submit([out_u8, labels])
+        return out_u8, labels
 
-    step_resident.n = 0
-
-    def finish_gathers():
-        while inflight:
-            inflight.pop(0).wait()
-
-    # end to end: every step copies its inputs (latent + one-hot mask) from pinned host memory and its images back;
-    # the copies of step i+1 / i-1 overlap the kernels of step i (e4s2024_b200/serving.py), as a serving loop would
-    # The mask crosses PCIe as the u8 label map the pipelines hold on the host and becomes one-hot on the device
-    # (utils.torch_utils.labelMap2OneHot, as in the reference's own flow: label map -> one-hot -> Generator).
-    from e4s2024_b200.serving import HostPipeline
-    # The images leave as the uint8 HWC arrays the pipelines build right after the generator (utils.torch_utils.tensor2im,
-    # face_swap_video_pipeline.py: `tensor2im(swapped_face_image[0])`), converted on the device with identical arithmetic.
-    from e4s2024_b200.utils.torch_utils import labelMap2OneHot, tensor2im_batch
-    labels_h = mask_h.argmax(1, keepdim=True).to(torch.uint8).pin_memory()          # [B,1,512,512]
-
-    def e2e_fn(lat, lab):
-        return tensor2im_batch(gen(lat, labelMap2OneHot(lab, K)))
-
-    pipe = HostPipeline(e2e_fn, dev)
+    pipe = HostPipeline(hot.run_shard_u8, dev)
 
     def run_e2e(steps):
         for _ in range(steps):
-            pipe.submit((latent_h, labels_h), out_h)
+            pipe.submit((img_h,), out_h)
         pipe.drain()
 
     def timed(fn, steps, whole=False):
@@ -325,8 +435,8 @@ def main():
         else:
             for _ in range(steps):
                 fn()
-            if world > 1:
-                finish_gathers()                         # every gather of the timed steps completes inside the timed region
+            if gather is not None:
+                gather.wait()                            # every gather of the timed steps completes inside the timed region
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -335,90 +445,99 @@ def main():
             dist.barrier()
         return float(ms.item())
 
+    step_resident()                                      # first pass also packs the weights
+    torch.cuda.synchronize()
+    n0 = L.launch_count()
+    out_u8, labels = step_resident()
+    launches_per_step = L.launch_count() - n0
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(step_resident, args.steps)
-    launches = args.steps * launches_per_forward         # kernels executed per step (a graph replay runs the same nodes)
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * BATCH * args.steps / (ms / 1e3)
-
     run_e2e(2)
     ms_e2e = timed(run_e2e, args.steps, whole=True)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / (ms / 1e3)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
 
     if os.environ.get("E4S_NCU"):          # one clean step for `ncu --profile-from-start off`
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         step_resident()
+        if gather is not None:
+            gather.wait()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
 
-    # ---- per-launch timing pass for the roofline of the dominant (convolution) kernel -----------------
-    E.PROFILE = []
-    step_resident()
-    torch.cuda.synchronize()
-    prof, E.PROFILE = E.PROFILE, None
-    if args.dump_layers and rank == 0:
-        with open(args.dump_layers, "w") as f:
-            for r in prof:
-                ms_l = r["ev"][0].elapsed_time(r["ev"][1])
-                f.write(json.dumps({"engine": r["engine"], "m": r["m"], "k": r["k"], "n": r["n"], "up2": r["up2"], "ms": round(ms_l, 4),
-                                    "exec_tflops": round(r["exec_flops"] / ms_l / 1e9, 2),
-                                    "io_gbs": round(r["bytes"] / ms_l / 1e6, 1)}) + "\n")
-    by = {}
-    for r in prof:
-        d = by.setdefault(r["engine"], {"ms": 0.0, "alg": 0.0, "exec": 0.0, "n": 0})
-        d["ms"] += r["ev"][0].elapsed_time(r["ev"][1])
-        d["alg"] += r["alg_flops"]
-        d["exec"] += r["exec_flops"]
-        d["n"] += 1
-    pk = peaks()
-    dom = max(by, key=lambda k: by[k]["ms"]) if by else None
-    roof = None
-    if dom:
-        d = by[dom]
-        ach = d["alg"] / (d["ms"] * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")       # dram bytes of the same 17 launches, one ncu --set full capture
-        if dom == "tc" and os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_step")
-        roof = {"bound": "tensor", "kernel": "conv_tc_{halo,wide,gather} kernels (tcgen05 bf16x3), the 17 convolution launches of one step" if dom == "tc" else "conv_igemm_f32_kernel (CUDA-core fp32)",
-                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic,
-                "peak_source": pk["source"], "launches": d["n"], "kernel_ms_per_step": d["ms"],
-                "executed_tflops": d["exec"] / (d["ms"] * 1e-3) / 1e12,
-                "note": "achieved = algorithmic conv FLOPs (each output pixel once, conv_transpose at input resolution) / summed "
-                        "CUDA-event durations of the conv launches of one step; the bf16x3 split issues 3 MMAs per product and "
-                        "the poly-phase up-convs execute 4x the algorithmic MACs (executed_tflops counts the latter, not the split)",
-                "by_engine": {k: {"ms": v["ms"], "launches": v["n"], "alg_tflops": v["alg"] / (v["ms"] * 1e-3) / 1e12} for k, v in by.items()}}
+    line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3-pass hi/lo split on tcgen05 tensor cores: bf16 pairs in the encoder / generator, fp16 pairs in BiSeNet; fp32 accumulate)"
+                     if E.conv_engine() == "tc" else "f32",
+            "data": "synthetic", "config": bench_config(world, E.conv_engine()), "clocks": clocks,
+            "gpu_launches": int(launches_per_step * args.steps),
+            "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e / args.steps,
+                    "note": "SwapHotPath.run_shard_u8 through serving.HostPipeline: pinned-host uint8 HWC images in (H2D every step), uint8 HWC images + "
+                            "u8 label maps out (D2H every step), double-buffered on copy streams; timed from the first H2D to the last D2H complete"
+                            + ("; every rank streams its own shard to / from host memory (no device all-gather on this leg)" if world > 1 else ""),
+                    "h2d_bytes_per_step": int(img_h.numel()) * world, "d2h_bytes_per_step": int(out_h[0].numel() + out_h[1].numel()) * world},
+            "alg_gflop_per_face": ALG_GFLOP_PER_FACE, "job_alg_tflops": value * ALG_GFLOP_PER_FACE / 1e3}
+    if gather is not None:
+        line["all_gather_bytes_per_rank_per_step"] = gather.bytes_per_rank()
 
-    used_graph = gg is not None
-    swap = None
-    if rank == 0 and world == 1 and not args.no_swap_path:
-        del G, pipe, gg
+    do_extras = rank == 0 and not args.no_extras
+    if (rank == 0 and not args.no_extras) or (rank == 0 and args.dump_layers):
+        stage_ms, prof = stage_breakdown(hot, img_d)
+        tp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")     # dram bytes of the same launches from one ncu capture of this command
+        traffic = json.load(open(tp)).get("dram_bytes_per_step") if os.path.exists(tp) else None
+        line["roofline"] = roofline_from(prof, BATCH, ms / args.steps, traffic)
+        if line["roofline"] is not None:
+            line["roofline"]["traffic_source"] = "profiles/r2_ncu_traffic.json (ncu capture of this command, sum over the step's convolution launches)" if traffic else None
+        line["stage_ms"] = stage_ms
+        if args.dump_layers and rank == 0:
+            with open(args.dump_layers, "w") as f:
+                for r in prof:
+                    ms_l = r["ev"][0].elapsed_time(r["ev"][1])
+                    f.write(json.dumps({"stage": r["stage"], "engine": r["engine"], "fmt": r["fmt"], "m": r["m"], "k": r["k"], "n": r["n"], "cin": r["cin"],
+                                        "hout": r["hout"], "kh": r["kh"], "stride": r["stride"], "up2": r["up2"], "ms": round(ms_l, 4),
+                                        "alg_tflops": round(r["alg_flops"] / ms_l / 1e9, 2), "exec_tflops": round(r["exec_flops"] / ms_l / 1e9, 2),
+                                        "io_gbs": round(r["bytes"] / ms_l / 1e6, 1)}) + "\n")
+    if do_extras and world == 1:
+        del pipe
+        torch.cuda.empty_cache()
+        for key, fn in (("configs", lambda: other_configs(hot, dev)), ("gpu_reference", lambda: gpu_reference(sds, img_d))):
+            try:
+                r = fn()
+                line.update(r) if key == "configs" else line.__setitem__(key, r)
+            except Exception as e:                      # a secondary line must never take the headline down with it
+                line[key] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    if rank == 0:
+        gpu_lab1 = labels[:1].cpu().numpy()
+        x01_1, x_1 = L.im2tensor(img_d[:1])
+        fimg = hot.run_shard(x_1, img01=x01_1)[0].cpu()          # fp32 image of face 0 (bit-identical to its slot in the batch)
+        if world == 1 and not args.no_extras:
+            try:
+                line["parity"] = label_parity(sds, img_h[:1], gpu_lab1)
+            except Exception as e:
+                line["parity"] = {"error": f"{type(e).__name__}: {e}"}
+        if not args.no_cpu_baseline and world == 1:
+            cpu, ref_img, ref_lab = cpu_baseline(sds, img_h[:1], gpu_lab1)
+            line["cpu_baseline"] = cpu
+            line.setdefault("parity", {})
+            line["parity"].update({"image_max_abs_diff_vs_cpu_oracle": float((fimg - ref_img).abs().max()), "image_abs_range": float(ref_img.abs().max()),
+                                   "image_tolerance": 1e-3, "faces_compared": 1})
+        else:
+            line["cpu_baseline"] = None
+    if do_extras and world == 1:
+        del hot
         torch.cuda.empty_cache()
         try:
-            swap = swap_path_line(dev)
-        except Exception as e:                          # the secondary line must never take the headline down with it
-            swap = {"error": f"{type(e).__name__}: {e}"}
+            line["generator_only"] = generator_only(dev, min(args.steps, 10))
+        except Exception as e:
+            line["generator_only"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_baseline()
-        line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if E.conv_engine() == "tc" else "f32",
-                "data": "synthetic",
-                "config": bench_config(world, E.conv_engine()),
-                "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": used_graph,
-                "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e / args.steps,
-                        "note": "labelMap2OneHot + Generator.forward + tensor2im_batch through HostPipeline: pinned-host H2D of every step's latent + u8 "
-                                "label map, D2H of its uint8 HWC images (the reference pipelines' tensor2im output), double-buffered on copy "
-                                "streams (timed region = first H2D to last D2H complete)",
-                        "h2d_bytes_per_step": int(latent_h.numel() * 4 + labels_h.numel()), "d2h_bytes_per_step": int(out_h.numel())},
-                "roofline": roof, "cpu_baseline": cpu, "swap_path": swap,
-                "alg_gflop_per_face": ALG_GFLOP_PER_FACE,
-                "job_alg_tflops": value * ALG_GFLOP_PER_FACE / 1e3}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -20,6 +20,7 @@ _ENGINE = os.environ.get("E4S_CONV_ENGINE", "tc")
 
 
 PROFILE = None        # set to a list by bench.py to time every conv launch with CUDA events
+PROFILE_STAGE = None  # label bench.py attaches to the launches it records ("parse" / "encoder" / "generator")
 TC_UNBIAS_OVERRIDE = None   # tests/micro/acc_bias.py: E4SConv.tc_unbias for every tensor-core launch (< 0 = no correction)
 
 
@@ -289,7 +290,8 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     ev0.record()
     launch()
     ev1.record()
-    PROFILE.append({"engine": "tc" if use_tc else "f32", "region_jobs": (region_jobs.count if region_jobs.count is not None else -1) if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
+    PROFILE.append({"stage": PROFILE_STAGE, "engine": "tc" if use_tc else "f32", "fmt": ("f16" if pw.tc_fmt == L.TC_F16 else "bf16") if use_tc else "f32",
+                    "cin": pw.cin, "hout": hout, "stride": stride, "kh": pw.kh, "region_jobs": (region_jobs.count if region_jobs.count is not None else -1) if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
                     "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1), "rgb": rgb is not None,
                     "bytes": 4.0 * (b * hin * win * pw.cin + (m_exec * pw.cout if out is not None else 0) + (3 * m_exec if rgb is not None else 0))})
     return out

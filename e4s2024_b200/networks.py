@@ -11,7 +11,7 @@ from . import _lib as L
 from . import engine as E
 from .encoders.psp_encoders import FSEncoder_PSP, RGB_PAD
 from .engine import View
-from .stylegan2.model import EqualLinear, Generator
+from .stylegan2.model import EqualLinear, Generator, grad_anchor, inference_only
 
 
 class LocalMLP(nn.Module):
@@ -111,8 +111,13 @@ class Net3(nn.Module):
         return self._bias_cache[1]
 
     # ---- public API (same signatures as the reference) ---------------------------------------------
-    @torch.no_grad()
     def forward(self, img, mask, resize=False, randomize_noise=True, return_latents=False):
+        anchor = grad_anchor(self, (img,))
+        with torch.no_grad():
+            out = self._forward_impl(img, mask, resize, randomize_noise, return_latents)
+        return inference_only(out, anchor)
+
+    def _forward_impl(self, img, mask, resize=False, randomize_noise=True, return_latents=False):
         codes_vector, structure_feats = self._encode(img, mask)
         codes = self._codes(codes_vector)
         images1, result_latent, structure_feats_GT = self.G([codes], structure_feats, mask, input_is_latent=True,
@@ -122,21 +127,41 @@ class Net3(nn.Module):
             return images1, structure_feats_GT, result_latent
         return images1, structure_feats_GT
 
-    @torch.no_grad()
     def get_style(self, img, mask):
+        anchor = grad_anchor(self, (img,))
+        with torch.no_grad():
+            out = self._get_style_impl(img, mask)
+        return inference_only(out, anchor)
+
+    def _get_style_impl(self, img, mask):
         codes_vector, structure_feats = self._encode(img, mask)
         return structure_feats, self._codes(codes_vector)
 
-    @torch.no_grad()
     def get_style_vectors(self, img, mask):
+        anchor = grad_anchor(self, (img,))
+        with torch.no_grad():
+            out = self._get_style_vectors_impl(img, mask)
+        return inference_only(out, anchor)
+
+    def _get_style_vectors_impl(self, img, mask):
         return self._encode(img, mask)
 
-    @torch.no_grad()
     def cal_style_codes(self, style_vectors):
+        anchor = grad_anchor(self, (style_vectors,))
+        with torch.no_grad():
+            out = self._cal_style_codes_impl(style_vectors)
+        return inference_only(out, anchor)
+
+    def _cal_style_codes_impl(self, style_vectors):
         return self._codes(style_vectors)
 
-    @torch.no_grad()
     def gen_img(self, struc_codes, style_codes, mask, randomize_noise=True, noise=None, return_latents=False):
+        anchor = grad_anchor(self, (style_codes,))
+        with torch.no_grad():
+            out = self._gen_img_impl(struc_codes, style_codes, mask, randomize_noise, noise, return_latents)
+        return inference_only(out, anchor)
+
+    def _gen_img_impl(self, struc_codes, style_codes, mask, randomize_noise=True, noise=None, return_latents=False):
         images, result_latent, structure_feats = self.G([style_codes], struc_codes, mask, input_is_latent=True,
                                                         randomize_noise=randomize_noise, noise=noise,
                                                         return_latents=return_latents, use_structure_code=False)

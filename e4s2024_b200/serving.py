@@ -60,14 +60,17 @@ class HostPipeline:
         slot = self.n_run % self.depth
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(self.ev_in[slot])
-        img = self.fn(*self.slots[slot])
+        res = self.fn(*self.slots[slot])
         self.ev_used[slot].record(cur)
         out_host = self.pending[slot]
         if out_host is not None:
+            # one result tensor -> one pinned host tensor, or a tuple of results -> a tuple of host tensors (images + label maps)
+            pairs = list(zip(res, out_host)) if isinstance(out_host, (tuple, list)) else [(res, out_host)]
             self.s_out.wait_event(self.ev_used[slot])
-            img.record_stream(self.s_out)
             with torch.cuda.stream(self.s_out):
-                out_host.copy_(img, non_blocking=True)
+                for d, h in pairs:
+                    d.record_stream(self.s_out)
+                    h.copy_(d, non_blocking=True)
                 self.ev_out[slot].record(self.s_out)
         self.n_run += 1
 
@@ -86,7 +89,8 @@ class GraphedGenerator:
         gg = GraphedGenerator(G, batch=16, regions=12, mask_hw=(512, 512))
         img = gg(latent, mask)        # img is the graph's static output buffer: consume (or copy) it before the next call
 
-    Noise: the registered buffers (`randomize_noise=False`), as the swap pipelines run the generator."""
+    Noise: the registered buffers (`randomize_noise=False`), as the swap pipelines run the generator.
+    Inputs must have exactly the captured shapes (no broadcasting into the static buffers)."""
 
     def __init__(self, G, batch: int, regions: int, mask_hw=(512, 512), device: Optional[torch.device] = None, warmup: int = 2):
         dev = device or next(G.parameters()).device
@@ -112,13 +116,25 @@ class GraphedGenerator:
         img, _, feats = self.G([self.latent], None, self.mask, input_is_latent=True, randomize_noise=False, _host_flag=self.flag)
         return img, feats
 
-    def __call__(self, latent: torch.Tensor, mask: torch.Tensor, check: bool = False) -> torch.Tensor:
+    def __call__(self, latent: torch.Tensor, mask: torch.Tensor, check: bool = True) -> torch.Tensor:
+        """check=True (default): wait for the replay and verify the mask was one-hot; a soft / overlapping / empty mask is re-run
+        through `Generator.forward` (generic per-region path), so the result is always the reference's.  check=False returns without
+        waiting (pipelined serving): the caller MUST call `verify()` before trusting the image."""
+        if tuple(mask.shape) != tuple(self.mask.shape):
+            raise ValueError(f"GraphedGenerator was captured for masks of shape {tuple(self.mask.shape)}, got {tuple(mask.shape)}")
+        if latent.dim() != 4 or latent.shape[:2] != self.latent.shape[:2] or latent.shape[3] != self.latent.shape[3] or \
+                latent.shape[2] < self.latent.shape[2]:
+            raise ValueError(f"GraphedGenerator was captured for latents of shape {tuple(self.latent.shape)}, got {tuple(latent.shape)}")
         self.latent.copy_(latent[:, :, :self.latent.shape[2]], non_blocking=True)    # like forward: extra W+ layers are ignored
         self.mask.copy_(mask, non_blocking=True)
         self.graph.replay()
-        if check:                                                    # optional: waits for the replay
-            torch.cuda.current_stream(self.latent.device).synchronize()
-            if int(self.flag[0]) != 0:
-                raise RuntimeError("GraphedGenerator: the mask is not one-hot; use Generator.forward (generic per-region path)")
+        if check and not self.verify():
+            img, _, _ = self.G([self.latent], None, self.mask, input_is_latent=True, randomize_noise=False)
+            return img
         return self.image
+
+    def verify(self) -> bool:
+        """Waits for the last replay; False if its mask was not one-hot (the graph's image is then NOT the reference's result)."""
+        torch.cuda.current_stream(self.latent.device).synchronize()
+        return int(self.flag[0]) == 0
 

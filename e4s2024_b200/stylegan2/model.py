@@ -418,10 +418,17 @@ class Generator(nn.Module):
     def get_latent(self, input):
         return self.style(input)
 
-    @torch.no_grad()
     def forward(self, styles, structure_feats, mask, return_latents=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
                 use_structure_code=False, _ctx=None, _host_flag=None):
+        anchor = grad_anchor(self, (styles,))
+        with torch.no_grad():
+            out = self._forward(styles, structure_feats, mask, return_latents, inject_index, truncation, truncation_latent,
+                                input_is_latent, noise, randomize_noise, use_structure_code, _ctx, _host_flag)
+        return inference_only(out, anchor)
+
+    def _forward(self, styles, structure_feats, mask, return_latents, inject_index, truncation, truncation_latent, input_is_latent,
+                 noise, randomize_noise, use_structure_code, _ctx, _host_flag):
         if not input_is_latent:
             styles = [self.style(s) for s in styles]
         if noise is None:
@@ -505,6 +512,47 @@ class Generator(nn.Module):
         if return_latents:
             return image, latent, intermediate_feats
         return image, None, intermediate_feats
+
+
+_NO_BACKWARD = ("the B200 drop-in is inference-only: there is no backward through the fused modulated convolution. Run PTI / training "
+                "on the reference modules and load the tuned weights here with load_state_dict().")
+
+
+class _InferenceOnly(torch.autograd.Function):
+    """Identity whose backward explains itself.  The kernels run under no_grad, so a caller that expects gradients (the reference video
+    pipeline's PTI step, training/video_swap_ft_coach.py:242-318: `loss.backward()` through net.G) would otherwise die inside autograd
+    with 'element 0 of tensors does not require grad'; forward-only callers are unaffected."""
+
+    @staticmethod
+    def forward(ctx, out, anchor):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise L.E4SError(_NO_BACKWARD)
+
+
+def grad_anchor(module: nn.Module, inputs=()):
+    """A tensor that requires grad among the inputs / parameters when autograd is recording, else None."""
+    if not torch.is_grad_enabled():
+        return None
+    for t in inputs:
+        for u in (t if isinstance(t, (list, tuple)) else (t,)):
+            if isinstance(u, torch.Tensor) and u.requires_grad:
+                return u
+    for p_ in module.parameters():
+        if p_.requires_grad:
+            return p_
+    return None
+
+
+def inference_only(outputs, anchor):
+    """Attach the explanatory backward to every floating-point tensor of `outputs` (a tuple as the modules return it)."""
+    if anchor is None:
+        return outputs
+    if isinstance(outputs, torch.Tensor):
+        return _InferenceOnly.apply(outputs, anchor)
+    return tuple(_InferenceOnly.apply(o, anchor) if isinstance(o, torch.Tensor) and o.is_floating_point() else o for o in outputs)
 
 
 def _batched_tables(plan):

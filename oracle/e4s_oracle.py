@@ -3,7 +3,10 @@
 A functional, state-dict driven restatement (plain PyTorch CPU ops, fp32 or fp64)
 of the reference algorithms on the hot path.  Nothing in the product package
 (`e4s2024_b200/`) may import this file; only `tests/`, `__graft_entry__.smoke()`
-and `bench.py`'s cpu_baseline / `--impl reference` legs do.
+and `bench.py`'s baseline legs do (cpu_baseline, `--impl reference`, and `gpu_reference`:
+the same torch ops -- the reference's K grouped cuDNN convolutions per masked layer --
+executed on the B200 as the "existing Blackwell path" the new kernels are compared with;
+every function follows the device of its inputs).
 
 Parity pinning: the reference holds no golden vectors for this path (SURVEY.md
 section 4), so the oracle is pinned against the reference's own modules executed in
@@ -30,9 +33,9 @@ SD = Dict[str, torch.Tensor]
 # --------------------------------------------------------------------------------------
 
 
-def fir_kernel(taps: Sequence[float], gain: float = 1.0, dtype=torch.float32) -> torch.Tensor:
+def fir_kernel(taps: Sequence[float], gain: float = 1.0, dtype=torch.float32, device=None) -> torch.Tensor:
     """models/stylegan2/model.py:23-31 (make_kernel): outer product, normalised to sum 1."""
-    k = torch.tensor(list(taps), dtype=dtype)
+    k = torch.tensor(list(taps), dtype=dtype, device=device)
     k2 = torch.outer(k, k)
     return k2 / k2.sum() * gain
 
@@ -106,7 +109,7 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, sd: SD, prefix: str, 
         y = F.conv_transpose2d(x.reshape(1, b * ci, h, w), wt, padding=0, stride=2, groups=b)
         y = y.reshape(b, co, y.shape[2], y.shape[3])
         p = (len(blur_taps) - 2) - (k - 1)
-        return upfirdn2d(y, fir_kernel(blur_taps, 4.0, x.dtype), pad=((p + 1) // 2 + 1, p // 2 + 1))
+        return upfirdn2d(y, fir_kernel(blur_taps, 4.0, x.dtype, x.device), pad=((p + 1) // 2 + 1, p // 2 + 1))
     y = F.conv2d(x.reshape(1, b * ci, h, w), wmod.reshape(b * co, ci, k, k), padding=k // 2, groups=b)
     return y.reshape(b, co, y.shape[2], y.shape[3])
 
@@ -142,7 +145,7 @@ def to_rgb(x, style, mask, skip, sd: SD, prefix: str, *, mask_op: bool,
     y = _regional(x, style, mask, fn, tuple(x.shape[2:])) if mask_op else fn(x, style)
     y = y + sd[prefix + "bias"].to(x.dtype)
     if skip is not None:
-        y = y + upfirdn2d(skip, fir_kernel(blur_taps, 4.0, x.dtype), up=2, pad=(2, 1))
+        y = y + upfirdn2d(skip, fir_kernel(blur_taps, 4.0, x.dtype, x.device), up=2, pad=(2, 1))
     return y
 
 
@@ -394,7 +397,7 @@ def bicubic_taps(factor: int, a: float = -0.5) -> torch.Tensor:
 
 def bicubic_downsample(x: torch.Tensor, factor: int) -> torch.Tensor:
     """face_parsing_demo.py:46-84: reflect pad, vertical then horizontal strided 1-D filter."""
-    k = bicubic_taps(factor).to(x.dtype)
+    k = bicubic_taps(factor).to(x)
     n = k.numel()
     c = x.shape[1]
     pad = n - factor
@@ -412,8 +415,8 @@ SEG_STD = (0.229, 0.224, 0.225)       # face_parsing/model.py:16
 def parser_preprocess(img01: torch.Tensor, size: int = 1024) -> torch.Tensor:
     """face_parsing_demo.py:151-160 for inputs >= 512: bicubic down to 512, clamp, normalise.
     img01 is the ToTensor() image batch [B,3,size,size] in [0,1]."""
-    mean = torch.tensor(SEG_MEAN, dtype=img01.dtype).reshape(1, 3, 1, 1)
-    std = torch.tensor(SEG_STD, dtype=img01.dtype).reshape(1, 3, 1, 1)
+    mean = torch.tensor(SEG_MEAN, dtype=img01.dtype, device=img01.device).reshape(1, 3, 1, 1)
+    std = torch.tensor(SEG_STD, dtype=img01.dtype, device=img01.device).reshape(1, 3, 1, 1)
     return (bicubic_downsample(img01, size // 512).clamp(0, 1) - mean) / std
 
 
@@ -427,14 +430,14 @@ for _src, _dst in ((12, 1), (13, 1), (2, 2), (3, 2), (4, 3), (5, 3), (17, 4), (1
 def face_parse(sd: SD, img01: torch.Tensor, convert_to_seg12: bool = True) -> np.ndarray:
     """face_parsing_demo.py:162-176,187-200 batched: labels uint8 [B,512,512]."""
     logits = bisenet_forward(sd, parser_preprocess(img01, img01.shape[-1]))[0]
-    seg = torch.argmax(logits, dim=1).numpy().astype(np.uint8)
+    seg = torch.argmax(logits, dim=1).cpu().numpy().astype(np.uint8)
     return SEG19_TO_SEG12[seg] if convert_to_seg12 else seg
 
 
 def label_to_onehot(label: torch.Tensor, num_cls: int) -> torch.Tensor:
     """utils/torch_utils.py:207-213 (labelMap2OneHot): [B,1,H,W] int64 -> [B,num_cls,H,W] float."""
     b, _, h, w = label.shape
-    return torch.zeros(b, num_cls, h, w).scatter_(1, label, 1.0)
+    return torch.zeros(b, num_cls, h, w, device=label.device).scatter_(1, label, 1.0)
 
 
 def swap_comp_style_vector(sv1: torch.Tensor, sv2: torch.Tensor, comp_indices, below_face_interpolation: bool = False) -> torch.Tensor:
@@ -450,6 +453,15 @@ def swap_comp_style_vector(sv1: torch.Tensor, sv2: torch.Tensor, comp_indices, b
     empty = sv2[:, 9, :].sum(dim=1) == 0                     # :364-365 source without a mouth region -> target's vector
     out[empty, 9, :] = sv1[empty, 9, :]
     return out
+
+
+def to_tensor_normalize(img_u8: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)) -> Tuple[torch.Tensor, torch.Tensor]:
+    """TO_TENSOR and Compose([TO_TENSOR, NORMALIZE]) (datasets/dataset.py:45, face_swap_video_pipeline.py:338-346), batched:
+    uint8 HWC [B,H,W,3] -> (x01 = v/255, (x01 - mean)/std), fp32 NCHW -- torchvision's `.to(float32).div(255)` and `.sub_(mean).div_(std)`."""
+    x01 = img_u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
+    m = torch.tensor(mean, dtype=torch.float32, device=img_u8.device).view(1, 3, 1, 1)
+    sd = torch.tensor(std, dtype=torch.float32, device=img_u8.device).view(1, 3, 1, 1)
+    return x01.contiguous(), x01.sub(m).div(sd).contiguous()
 
 
 def tensor2im_u8(var: torch.Tensor, is_zero_center: bool = True) -> torch.Tensor:

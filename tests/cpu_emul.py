@@ -231,6 +231,12 @@ def tensor2im_u8(x, zero_center=True):
     return v.permute(0, 2, 3, 1).to(torch.uint8).contiguous()
 
 
+def im2tensor(x, want01=True, want_norm=True, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    x01 = x.permute(0, 3, 1, 2).float().div(255).contiguous()
+    xn = ((x01 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)).contiguous()
+    return (x01 if want01 else None), (xn if want_norm else None)
+
+
 def swap_comp_styles(target, source, comp_mask, below_face):
     """e4s_swap_comp_styles_f32 restated with torch (mode per component: target / source / average)."""
     out = target.clone()
@@ -363,7 +369,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
 
 
 _NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "upfirdn2d_general", "bias_act", "bias_act_grad", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
-          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
+          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "im2tensor", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
 

@@ -125,6 +125,12 @@ def test_swap_comp_style_vector(golden):
         close(y, g[f"y{i}"], 0.0)
 
 
+def test_im2tensor(golden):
+    g = golden("im2tensor")
+    x01, xn = orc.to_tensor_normalize(T(g["x"]))
+    assert float((x01 - T(g["y01"])).abs().max()) == 0.0 and float((xn - T(g["ynorm"])).abs().max()) == 0.0
+
+
 def test_tensor2im(golden):
     g = golden("tensor2im")
     assert int((orc.tensor2im_u8(T(g["x"])).numpy() != g["y"]).sum()) == 0

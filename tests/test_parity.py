@@ -39,7 +39,7 @@ def load(mod, shapes_seed, dev):
 
 
 def maxdiff(a, b):
-    return float((torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu()).abs().max())
+    return float((torch.as_tensor(a).detach().double().cpu() - torch.as_tensor(b).detach().double().cpu()).abs().max())
 
 
 @pytest.mark.parametrize("dev", DEVS)
@@ -127,6 +127,15 @@ def test_generator_small(golden, dev, tag):
     assert lat is None and img.shape == (2, 3, size, size)
     assert maxdiff(img, g["image"]) < 1e-3
     assert maxdiff(inter[:, ::16], g["inter"]) < 1e-3
+    # parameters that require grad + autograd recording (what the reference pipeline's PTI step does): the forward still works
+    # like the reference's, and backward fails with a message that says why (not autograd's "does not require grad")
+    from e4s2024_b200._lib import E4SError
+    assert img.requires_grad
+    with pytest.raises(E4SError, match="inference-only"):
+        img.mean().backward()
+    with torch.no_grad(), ctx_for(dev):
+        img2 = G([to(dev, latent)], None, to(dev, mask), input_is_latent=True, randomize_noise=False)[0]
+    assert not img2.requires_grad and maxdiff(img2, img) == 0.0
 
 
 @pytest.mark.parametrize("dev", DEVS)
@@ -224,6 +233,16 @@ def test_tensor2im_batch(golden, dev):
         y = tensor2im_batch(to(dev, T(g["x"])))
     assert y.dtype == torch.uint8 and tuple(y.shape) == g["y"].shape
     assert int((y.cpu().numpy() != g["y"]).sum()) == 0
+
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_im2tensor(golden, dev):
+    """TO_TENSOR / NORMALIZE on the device, the same floats as torchvision's (every byte value covered)."""
+    from e4s2024_b200 import _lib as L
+    g = golden("im2tensor")
+    with ctx_for(dev):
+        y01, yn = L.im2tensor(to(dev, T(g["x"])))
+    assert maxdiff(y01, g["y01"]) == 0.0 and maxdiff(yn, g["ynorm"]) == 0.0
 
 
 MORPH_CASES = {"ones5": dict(kernel=torch.ones(5, 5)),

@@ -48,6 +48,13 @@ def test_graphed_generator_bit_exact():
         ref = G([lat], None, msk, input_is_latent=True, randomize_noise=False)[0]
         assert torch.equal(out, ref), float((out - ref).abs().max())
     soft = msk.clone()
-    soft[:, :, :8, :8] = 0.25                                        # not one-hot: the graph must refuse, not return a wrong image
-    with pytest.raises(RuntimeError):
-        gg(lat, soft, check=True)
+    soft[:, :, :8, :8] = 0.25                                        # not one-hot: never a wrong image -- the default call falls
+    out = gg(lat, soft)                                              # back to Generator.forward's generic per-region path
+    ref = G([lat], None, soft, input_is_latent=True, randomize_noise=False)[0]
+    assert torch.equal(out, ref)
+    gg(lat, soft, check=False)                                       # pipelined form: the caller must ask
+    assert gg.verify() is False
+    gg(lat, msk, check=False)
+    assert gg.verify() is True
+    with pytest.raises(ValueError):                                  # no silent broadcast of a batch-1 input into the static buffers
+        gg(lat[:1], msk[:1])
