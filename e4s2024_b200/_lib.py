@@ -50,7 +50,7 @@ class E4SConv(C.Structure):
 
 EXPORTS = [
     "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs",
-    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_pack_weights_tc_fmt", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_pack_weights_tc_fmt", "e4s_pack_conv_weights_f32", "e4s_pack_upconv_weights_f32", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_bias_act_grad_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
@@ -151,6 +151,26 @@ def pack_weights_tc(w_f32: torch.Tensor, phases: int, k: int, cin: int, cout: in
     out = torch.empty(nbytes, dtype=torch.uint8, device=w_f32.device)
     _check(lib().e4s_pack_weights_tc_fmt(C.c_void_p(w_f32.data_ptr()), phases, k, cin, cout, cout_pad, int(fmt), _f32(scale),
                                          C.c_void_p(out.data_ptr()), _stream()), "e4s_pack_weights_tc_fmt")
+    return out
+
+
+def pack_conv_weights(w: torch.Tensor, cin_pad: int, cout_pad: int, scale: float = 1.0, sumsq: bool = False) -> torch.Tensor:
+    """w [Co,Ci,kh,kw] -> [1, kh*kw*cin_pad, cout_pad] fp32 (sumsq: [1, cin_pad, cout_pad] = sum_taps (scale*w)^2)."""
+    _req(w)
+    co, ci, kh, kw = w.shape
+    out = torch.empty(1, (1 if sumsq else kh * kw) * cin_pad, cout_pad, device=w.device, dtype=torch.float32)
+    _check(lib().e4s_pack_conv_weights_f32(_fp(w.data_ptr()), _fp(out.data_ptr()), co, ci, kh, kw, cin_pad, cout_pad, _f32(scale), int(sumsq),
+                                           _stream()), "e4s_pack_conv_weights_f32")
+    return out
+
+
+def pack_upconv_weights(w: torch.Tensor, fir: torch.Tensor, cout_pad: int, scale: float = 1.0) -> torch.Tensor:
+    """w [Co,Ci,3,3], fir [4,4] -> [4, 9*Ci, cout_pad] fp32 phase filters."""
+    _req(w), _req(fir)
+    co, ci = w.shape[:2]
+    out = torch.empty(4, 9 * ci, cout_pad, device=w.device, dtype=torch.float32)
+    _check(lib().e4s_pack_upconv_weights_f32(_fp(w.data_ptr()), _fp(fir.data_ptr()), _fp(out.data_ptr()), co, ci, cout_pad, _f32(scale),
+                                             _stream()), "e4s_pack_upconv_weights_f32")
     return out
 
 

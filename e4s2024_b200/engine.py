@@ -94,15 +94,13 @@ def tc_available() -> bool:
 
 def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, phases: int, want_tc: bool,
                  tc_fmt: int = L.TC_BF16) -> PackedConv:
-    cout_pad = pad_to(cout, 4)
-    if cout_pad != cout:
-        w_pkc = torch.nn.functional.pad(w_pkc, (0, cout_pad - cout))
-    w_pkc = w_pkc.contiguous().float()
+    """w_pkc: [phases, K, cout_pad] fp32 from L.pack_conv_weights / L.pack_upconv_weights."""
+    cout_pad = w_pkc.shape[2]
     pc = PackedConv(w_pkc, cin, cout, cout_pad, kh, kw, phases)
     if want_tc and w_pkc.is_cuda and tc_eligible(cin, cout) and tc_available():
         scale = 1.0
         if tc_fmt == L.TC_F16:
-            # fp16 operands: bring max|w| to [2^13, 2^14) with a power of two (exact), so that the lo parts of all but the
+            # fp16 operands: bring max|w| to [2^13, 2^14) with a power of two (exact), so that the hi parts of all but the
             # tiniest weights stay normal fp16 numbers; the launch undoes it through E4SConv.tc_out_scale
             mx = float(w_pkc.abs().max())
             if mx > 0.0 and math.isfinite(mx):
@@ -112,49 +110,29 @@ def _finish_pack(w_pkc: torch.Tensor, cin: int, cout: int, kh: int, kw: int, pha
     return pc
 
 
-def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, want_tc: bool = True, tc_fmt: int = L.TC_BF16) -> PackedConv:
-    """w [Co,Ci,kh,kw] -> k = (ky*kw + kx)*Ci_pad + ci rows, co contiguous."""
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, want_tc: bool = True, tc_fmt: int = L.TC_BF16,
+                     scale: float = 1.0, sumsq: bool = False) -> PackedConv:
+    """w [Co,Ci,kh,kw] -> k = (ky*kw + kx)*Ci_pad + ci rows, co contiguous (one kernel: e4s_pack_conv_weights_f32).
+    sumsq: the [Ci] x [Co] matrix sum_taps (scale*w)^2 instead (demodulation table GEMM)."""
     co, ci, kh, kw = w.shape
     cin = ci if cin_pad is None else cin_pad
-    t = w.detach().permute(2, 3, 1, 0)                      # [kh,kw,Ci,Co]
-    if cin != ci:
-        t = torch.nn.functional.pad(t, (0, 0, 0, cin - ci))
-    return _finish_pack(t.reshape(1, kh * kw * cin, co), cin, co, kh, kw, 1, want_tc, tc_fmt)
+    m = L.pack_conv_weights(w.detach().contiguous().float(), cin, pad_to(co, 4), scale, sumsq)
+    if sumsq:
+        return _finish_pack(m, cin, co, 1, 1, 1, False)
+    return _finish_pack(m, cin, co, kh, kw, 1, want_tc, tc_fmt)
 
 
-def pack_linear_weight(w: torch.Tensor, want_tc: bool = False) -> PackedConv:
+def pack_linear_weight(w: torch.Tensor, want_tc: bool = False, scale: float = 1.0) -> PackedConv:
     """w [out,in] (F.linear) as a 1x1 conv."""
-    return pack_conv_weight(w.detach()[:, :, None, None], want_tc=want_tc)
+    return pack_conv_weight(w.detach()[:, :, None, None], want_tc=want_tc, scale=scale)
 
 
-def polyphase_weights(w: torch.Tensor, fir: torch.Tensor) -> torch.Tensor:
-    """conv_transpose2d(stride 2, weight w[Co,Ci,3,3] used as [Ci,Co,3,3]) followed by upfirdn2d(fir 4x4, pad=(1,1))
-    == four 3x3 phase filters applied at input resolution (re-derived):
-      out[2A+py, 2B+px] = sum_{u,v} x[A-1+u, B-1+v] * Wph[py,px,u,v]
-      Wph[py,px,u,v] = sum_{m,n} w[ky,kx] * fir_flipped[m,n],  ky = 2(1-u)+py+m-1, kx likewise, 0<=ky,kx<=2.
-    Returns [2,2,3,3,Ci,Co]."""
+def pack_up_weight(w: torch.Tensor, fir: torch.Tensor, want_tc: bool = True, scale: float = 1.0) -> PackedConv:
+    """conv_transpose2d(stride 2, weight w[Co,Ci,3,3] used as [Ci,Co,3,3]) followed by upfirdn2d(fir 4x4, pad=(1,1)) as four 3x3
+    phase filters applied at input resolution (one kernel: e4s_pack_upconv_weights_f32)."""
     co, ci = w.shape[:2]
-    kf = torch.flip(fir.to(w.dtype), [0, 1])
-    out = w.new_zeros(2, 2, 3, 3, ci, co)
-    for py in range(2):
-        for u in range(3):
-            for m in range(4):
-                ky = 2 * (1 - u) + py + m - 1
-                if not 0 <= ky <= 2:
-                    continue
-                for px in range(2):
-                    for v in range(3):
-                        for n in range(4):
-                            kx = 2 * (1 - v) + px + n - 1
-                            if 0 <= kx <= 2:
-                                out[py, px, u, v] += w[:, :, ky, kx].t() * kf[m, n]
-    return out
-
-
-def pack_up_weight(w: torch.Tensor, fir: torch.Tensor, want_tc: bool = True) -> PackedConv:
-    co, ci = w.shape[:2]
-    ph = polyphase_weights(w.detach(), fir)                 # [2,2,3,3,Ci,Co]
-    return _finish_pack(ph.reshape(4, 9 * ci, co), ci, co, 3, 3, 4, want_tc)
+    m = L.pack_upconv_weights(w.detach().contiguous().float(), fir.detach().contiguous().float().to(w.device), pad_to(co, 4), scale)
+    return _finish_pack(m, ci, co, 3, 3, 4, want_tc)
 
 
 class View:

@@ -91,7 +91,7 @@ class EqualLinear(nn.Module):
     def packed(self):
         key = _ver(self.weight) + (_ver(self.bias) if self.bias is not None else ())
         if self._pack is None or self._pack[0] != key:
-            pw = E.pack_linear_weight(self.weight.detach() * self.scale)
+            pw = E.pack_linear_weight(self.weight.detach(), scale=self.scale)
             b = None if self.bias is None else (self.bias.detach() * self.lr_mul).contiguous()
             self._pack = (key, pw, b)
         return self._pack[1], self._pack[2]
@@ -165,16 +165,16 @@ class ModulatedConv2d(nn.Module):
     def packed(self):
         key = _ver(self.weight) + ((_ver(self.blur.kernel)) if self.upsample else ())
         if self._pack is None or self._pack[0] != key:
-            w = (self.weight.detach()[0] * self.scale).float()                    # [Co,Ci,k,k]
+            w = self.weight.detach()[0].float()                                   # [Co,Ci,k,k]; scale is applied by the pack kernels
             if self.upsample:
                 if self.kernel_size != 3 or tuple(self.blur.kernel.shape) != (4, 4) or self.blur.pad != (1, 1):
                     raise L.E4SError("up-sampling ModulatedConv2d supports kernel_size=3 with a 4-tap blur")
-                conv = E.pack_up_weight(w, self.blur.kernel.detach().to(w.device))
+                conv = E.pack_up_weight(w, self.blur.kernel, scale=self.scale)
             else:
-                conv = E.pack_conv_weight(w)
+                conv = E.pack_conv_weight(w, scale=self.scale)
             wsq = None
             if self.demodulate:                                                   # sum_taps (scale*W)^2 -> [Ci] x [Co]
-                wsq = E.pack_conv_weight(w.pow(2).sum(dim=(2, 3))[:, :, None, None], want_tc=False)
+                wsq = E.pack_conv_weight(w, scale=self.scale, sumsq=True)
             self._pack = (key, conv, wsq)
         return self._pack[1], self._pack[2]
 

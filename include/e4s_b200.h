@@ -155,6 +155,16 @@ int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cin, int cout
 int e4s_pack_weights_tc_fmt(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, int fmt, float scale, void* w_packed,
                             void* stream);
 
+/* nn.Module weights -> the engine's fp32 matrices, one launch per layer.
+ * e4s_pack_conv_weights_f32: w [cout][cin][kh][kw] (nn.Conv2d / F.linear weight with kh = kw = 1) -> out [kh*kw*cin_pad][cout_pad],
+ *   out[tap*cin_pad + ci][co] = scale * w[co][ci][tap], zero in the channel padding.  sumsq != 0: out [cin_pad][cout_pad] =
+ *   sum_taps (scale*w)^2, the weight of the demodulation table GEMM (reference models/stylegan2/model.py:279-281).
+ * e4s_pack_upconv_weights_f32: w [cout][cin][3][3] + the 4x4 blur kernel -> the four 3x3 phase filters of conv_transpose2d(stride 2)
+ *   + Blur(pad=(1,1)) (model.py:287-300), out [4][9*cin][cout_pad]. */
+int e4s_pack_conv_weights_f32(const float* w, float* out, int cout, int cin, int kh, int kw, int cin_pad, int cout_pad, float scale,
+                              int sumsq, void* stream);
+int e4s_pack_upconv_weights_f32(const float* w, const float* fir, float* out, int cout, int cin, int cout_pad, float scale, void* stream);
+
 /* upfirdn2d on NCHW fp32 [planes, in_h, in_w] (planes = B*C). kernel [kh,kw] is correlated FLIPPED. */
 int e4s_upfirdn2d_f32(const float* x, const float* kernel, float* out, int64_t planes, int in_h, int in_w,
                       int kh, int kw, int up_x, int up_y, int down_x, int down_y,

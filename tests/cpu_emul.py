@@ -140,6 +140,39 @@ def pack_weights_tc(w, phases, k, cin, cout, cout_pad, fmt=0, scale=1.0):
     return None
 
 
+def pack_conv_weights(w, cin_pad, cout_pad, scale=1.0, sumsq=False):
+    """e4s_pack_conv_weights_f32 restated with torch: [1, taps*cin_pad, cout_pad]."""
+    co, ci, kh, kw = w.shape
+    ws = w.float() * scale
+    if sumsq:
+        t = ws.pow(2).sum(dim=(2, 3)).t()[None]                                   # [1,Ci,Co]
+        return torch.nn.functional.pad(t, (0, cout_pad - co, 0, cin_pad - ci)).contiguous()
+    t = ws.permute(2, 3, 1, 0)                                                    # [kh,kw,Ci,Co]
+    t = torch.nn.functional.pad(t, (0, cout_pad - co, 0, cin_pad - ci))
+    return t.reshape(1, kh * kw * cin_pad, cout_pad).contiguous()
+
+
+def pack_upconv_weights(w, fir, cout_pad, scale=1.0):
+    """e4s_pack_upconv_weights_f32 restated with torch (the derivation of SURVEY.md appendix B.1): [4, 9*Ci, cout_pad]."""
+    co, ci = w.shape[:2]
+    ws = w.float() * scale
+    kf = torch.flip(fir.float(), [0, 1])
+    out = ws.new_zeros(2, 2, 3, 3, ci, co)
+    for py in range(2):
+        for u in range(3):
+            for m in range(4):
+                ky = 2 * (1 - u) + py + m - 1
+                if not 0 <= ky <= 2:
+                    continue
+                for px in range(2):
+                    for v in range(3):
+                        for n in range(4):
+                            kx = 2 * (1 - v) + px + n - 1
+                            if 0 <= kx <= 2:
+                                out[py, px, u, v] += ws[:, :, ky, kx].t() * kf[m, n]
+    return torch.nn.functional.pad(out.reshape(4, 9 * ci, co), (0, cout_pad - co)).contiguous()
+
+
 def upfirdn2d(x, kernel, up, down, pad0, pad1):
     from oracle import e4s_oracle as orc
     return orc.upfirdn2d(x, kernel, up, down, (pad0, pad1)).contiguous()
@@ -368,7 +401,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
     return nchw_to_nhwc(y, c_pad)
 
 
-_NAMES = ["conv", "conv_batched", "pack_weights_tc", "upfirdn2d", "upfirdn2d_general", "bias_act", "bias_act_grad", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
+_NAMES = ["conv", "conv_batched", "pack_weights_tc", "pack_conv_weights", "pack_upconv_weights", "upfirdn2d", "upfirdn2d_general", "bias_act", "bias_act_grad", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
           "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "im2tensor", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]

@@ -108,3 +108,26 @@ def test_tc_matches_f32_and_torch(case):
     dtc = float((ytc.permute(0, 3, 1, 2).double() - ref).abs().max())
     print(f"{name}: vs torch fp64: f32 engine {d32:.3e}, tc engine {dtc:.3e}")
     assert d32 < 2e-5 * max(scale, 1.0) and dtc < 2e-4 * max(scale, 1.0)
+
+
+def test_weight_pack_kernels_match_the_torch_derivation():
+    """e4s_pack_conv_weights_f32 / e4s_pack_upconv_weights_f32 (one launch per layer) against the torch restatement in
+    tests/cpu_emul.py (the poly-phase derivation of SURVEY.md appendix B.1, itself checked against the reference's
+    conv_transpose2d + Blur by the modconv goldens)."""
+    from e4s2024_b200 import _lib as L
+    from tests import cpu_emul
+    g = torch.Generator().manual_seed(3)
+    for co, ci, k, cin_pad in ((19, 24, 1, 24), (64, 3, 7, 8), (32, 16, 3, 16)):
+        w = torch.randn(co, ci, k, k, generator=g)
+        cout_pad = (co + 3) // 4 * 4
+        got = L.pack_conv_weights(w.cuda(), cin_pad, cout_pad, 0.37).cpu()
+        assert torch.equal(got, cpu_emul.pack_conv_weights(w, cin_pad, cout_pad, 0.37))
+        got = L.pack_conv_weights(w.cuda(), cin_pad, cout_pad, 0.37, True).cpu()
+        want = cpu_emul.pack_conv_weights(w, cin_pad, cout_pad, 0.37, True)
+        assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    w = torch.randn(12, 16, 3, 3, generator=g)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    fir = torch.outer(k1, k1) / 64 * 4
+    got = L.pack_upconv_weights(w.cuda(), fir.cuda(), 12, 0.25).cpu()
+    want = cpu_emul.pack_upconv_weights(w, fir, 12, 0.25)
+    assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
