@@ -99,9 +99,18 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def check_device(t: torch.Tensor):
+    """Kernels are enqueued on the CURRENT device's stream: a tensor that lives on another GPU would be dereferenced by the wrong
+    device.  One process per GPU with torch.cuda.set_device (bench.py, sharding.py) never trips this."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise E4SError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: wrap the call in "
+                       f"`with torch.cuda.device({t.device.index}):` or call torch.cuda.set_device first")
+
+
 def _req(t: torch.Tensor, dtype=torch.float32, contig: bool = True):
     if not t.is_cuda:
         raise E4SError("e4s2024_b200 kernels need CUDA tensors (no CPU fallback)")
+    check_device(t)
     if t.dtype != dtype:
         raise E4SError(f"expected {dtype}, got {t.dtype}")
     if contig and not t.is_contiguous():

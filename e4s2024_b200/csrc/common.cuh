@@ -26,6 +26,15 @@ inline int check_launch(const char* what) {
     if (!(cond)) return ::e4s::fail(E4S_ERR_ARG, __VA_ARGS__);   \
   } while (0)
 
+// Per-device one-time state (cudaFuncSetAttribute is per device; a process may drive several GPUs): index of the calling thread's
+// current device, clamped to the table size.
+constexpr int E4S_MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < E4S_MAX_DEVICES ? dev : E4S_MAX_DEVICES - 1;
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

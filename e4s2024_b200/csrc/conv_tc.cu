@@ -446,7 +446,8 @@ static bool tc_shape_ok(int k, int cout) {
 
 template <int BN>
 static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStream_t s) {
-  static bool attr_set = false;
+  static bool attr_set_dev[E4S_MAX_DEVICES] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(128) region_tile_jobs_kernel(const uint8_t* __
   }
 }
 
-static int g_halo_sm_count = 0;
+static int g_halo_sm_count_dev[E4S_MAX_DEVICES] = {};
 static int g_halo_cluster = -1;
 
 // geometry the halo kernel takes (everything else stays on the gather kernel)
@@ -727,7 +727,8 @@ bool tc_halo_eligible(const E4SConv* p) {
 template <int BN, bool UP, bool C32 = false>
 static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const int4* rjobs = nullptr, const int* rjob_count = nullptr,
                        int rjob_host_count = 0) {
-  static bool attr_set = false;
+  static bool attr_set_dev[E4S_MAX_DEVICES] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   constexpr int pm = hl_phase_merge(BN, UP);
   constexpr int smem_bytes = hl_smem_bytes(BN, pm);
   if (!attr_set) {
@@ -735,6 +736,7 @@ static int launch_halo(const E4SConv* p, const void* wpk, cudaStream_t s, const 
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  int& g_halo_sm_count = g_halo_sm_count_dev[current_device_slot()];
   if (g_halo_sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -447,7 +447,8 @@ static int g_wide_pair = -1;
 
 template <bool UP, bool PAIR>
 static int launch_wide_t(const E4SConv* p, const void* wpk, cudaStream_t s) {
-  static bool attr_set = false;
+  static bool attr_set_dev[E4S_MAX_DEVICES] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wide_kernel<UP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM);
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc(wide): cudaFuncSetAttribute: %s", cudaGetErrorString(e));

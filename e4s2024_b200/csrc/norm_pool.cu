@@ -152,7 +152,8 @@ constexpr int MM_PY = 16;          // pixel rows per CTA (512 threads): the kern
 
 __global__ void __launch_bounds__(32 * MM_PY) masked_mean_kernel(const float* __restrict__ feat, int64_t f_pitch, int h, int w,
                                                                  int c, const float* __restrict__ mask, int k, int mh, int mw,
-                                                                 float* __restrict__ codes, int64_t sb, int64_t sk, int c_off) {
+                                                                 float* __restrict__ codes, int64_t sb, int64_t sk, int c_off,
+                                                                 int k_total, int k0) {
   __shared__ double red[MM_PY][32];
   __shared__ int redc[MM_PY];
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(32 * MM_PY) masked_mean_kernel(const float* __
     acc[j] = 0.0;
     cnt[j] = 0;
   }
-  const float* mb = mask + (int64_t)b * k * mh * mw;
+  const float* mb = mask + ((int64_t)b * k_total + k0) * mh * mw;     // regions k0 .. k0 + k - 1 of this sample
   // Two pixels per step, all 2k mask taps and both feature values loaded BEFORE any of them is tested: the first
   // version branched on each mask load (k dependent L2 round trips per pixel, 1.4 ms per call at 64^2 x 256 channels).
   // Each thread still adds its pixels in increasing order and adding 0.0 for the regions a pixel is not in leaves the sums
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(32 * MM_PY) masked_mean_kernel(const float* __
         s += red[i][cx];
         n += redc[i];
       }
-      codes[(int64_t)b * sb + (int64_t)j * sk + c_off + ch] = n > 0 ? (float)(s / n) : 0.f;
+      codes[(int64_t)b * sb + (int64_t)(k0 + j) * sk + c_off + ch] = n > 0 ? (float)(s / n) : 0.f;
     }
   }
 }
@@ -299,11 +300,16 @@ extern "C" int e4s_masked_mean_f32(const float* feat, int64_t f_pitch, int batch
                                    int mh, int mw, float* codes, int64_t codes_stride_b, int64_t codes_stride_k, int c_off,
                                    void* stream) {
   E4S_REQUIRE(feat && mask && codes && batch > 0 && h > 0 && w > 0 && c > 0, "masked_mean: bad args");
-  E4S_REQUIRE(k > 0 && k <= MM_MAXK && mh > 0 && mw > 0, "masked_mean: k must be in 1..%d", MM_MAXK);
+  E4S_REQUIRE(k > 0 && mh > 0 && mw > 0, "masked_mean: bad mask shape");
   dim3 grid(ceil_div(c, 32), batch);
-  masked_mean_kernel<<<grid, 32 * MM_PY, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, mask, k, mh, mw, codes, codes_stride_b,
-                                                         codes_stride_k, c_off);
-  return check_launch("masked_mean");
+  int rc = E4S_OK;
+  for (int k0 = 0; k0 < k && rc == E4S_OK; k0 += MM_MAXK) {       // MM_MAXK regions per launch (the 19-class UI variant takes two)
+    const int kn = k - k0 < MM_MAXK ? k - k0 : MM_MAXK;
+    masked_mean_kernel<<<grid, 32 * MM_PY, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, mask, kn, mh, mw, codes, codes_stride_b,
+                                                           codes_stride_k, c_off, k, k0);
+    rc = check_launch("masked_mean");
+  }
+  return rc;
 }
 
 extern "C" int e4s_maxpool3x3s2_nhwc_f32(const float* x, int batch, int h, int w, int c, float* y, void* stream) {

@@ -27,6 +27,7 @@ class FSEncoder_PSP(nn.Module):
             for bottleneck in block:
                 modules.append(bottleneck_IR_SE_Ours(bottleneck.in_channel, bottleneck.depth, bottleneck.stride))
         self.body = nn.Sequential(*modules)
+        E.install_pack_invalidation(self)
 
     def get_per_comp_styleCode(self, style_feats, segmap):
         """psp_encoders.py:355-375 on NCHW feats: per-(sample, region) masked mean, zeros for empty regions."""

@@ -34,6 +34,25 @@ def conv_engine() -> str:
     return _ENGINE
 
 
+_PACK_ATTRS = ("_pack", "_e4s_pack", "_e4s_affine", "_wrgb", "_bias_cache")
+
+
+def invalidate_packs(module: torch.nn.Module):
+    """Drop every cached engine packing (packed / tensor-core weights, folded BatchNorm, ToRGB rows, MLP biases) under `module`.
+    The caches are keyed on (data_ptr, _version) of the parameters, which in-place updates through `.data` do NOT change (the
+    reference's Ranger optimiser and EMA `accumulate` write weights exactly that way): call this after such an update.
+    `load_state_dict` on the drop-in modules calls it automatically."""
+    for m in module.modules():
+        for a in _PACK_ATTRS:
+            if getattr(m, a, None) is not None:
+                setattr(m, a, None)
+
+
+def install_pack_invalidation(module: torch.nn.Module):
+    """load_state_dict(...) -> invalidate_packs (registered by Generator / Net3 / FSEncoder_PSP / BiSeNet)."""
+    module.register_load_state_dict_post_hook(lambda mod, incompatible: invalidate_packs(mod))
+
+
 def pad_to(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
@@ -171,6 +190,8 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     adds the fused ToRGB tail (halo kernel only, see rgb_fusable); with store_out=False the activations are never written."""
     b, hin, win = x.bhw
     assert x.c == pw.cin, (x.c, pw.cin)
+    if x.t.is_cuda:
+        L.check_device(x.t)
     pad = (pw.kh // 2) if pad is None else pad
     if up2:
         hout, wout = 2 * hin, 2 * win

@@ -79,14 +79,15 @@ class FaceParser(nn.Module):
         return (self.downsample.taps.to(dev), seg_mean.reshape(3).to(dev), seg_std.reshape(3).to(dev))
 
     def preprocess_tensor(self, im01: torch.Tensor) -> torch.Tensor:
-        """[B,3,S,S] in [0,1] on the GPU -> normalised NHWC [B,512,512,RGB_PAD] (face_parsing_demo.py:151-160)."""
+        """[B,3,S,S] in [0,1] on the GPU, S >= 512 -> normalised NHWC [B,S/f,S/f,RGB_PAD] with the FIXED factor f = self.size // 512
+        of face_parsing_demo.py:138-139,151-156 (a 1024^2 parser given a 512^2 image parses at 256^2, like the reference)."""
         taps, mean, std = self._consts(im01.device)
-        if im01.shape[-1] >= 512:
-            factor = im01.shape[-1] // 512
-            if factor == self.downsample.factor:
-                return L.bicubic_down_norm(im01.contiguous().float(), factor, taps, mean, std, RGB_PAD)
-            return L.bicubic_down_norm(im01.contiguous().float(), factor, bicubic_taps(factor).to(im01.device), mean, std, RGB_PAD)
-        raise L.E4SError("inputs smaller than 512 go through preprocess_img (PIL resize)")
+        s, f = im01.shape[-1], self.downsample.factor
+        if im01.shape[-2] != s or s < 512:
+            raise L.E4SError("inputs smaller than 512 (or not square) go through preprocess_img (PIL resize)")
+        if s % f or (s // f) % 32:
+            raise L.E4SError(f"a {s}x{s} input down-sampled by {f} must be a multiple of 32 for BiSeNet")
+        return L.bicubic_down_norm(im01.contiguous().float(), f, taps, mean, std, RGB_PAD)
 
     def preprocess_img(self, img):
         """PIL image -> normalised NHWC tensor."""
@@ -102,20 +103,21 @@ class FaceParser(nn.Module):
 
     @torch.no_grad()
     def parse_batch(self, im01: torch.Tensor, convert_to_seg12: bool = True) -> torch.Tensor:
-        """Batched GPU entry point: [B,3,S,S] in [0,1] -> u8 labels [B,512,512] (12-region ids by default)."""
+        """Batched GPU entry point: [B,3,S,S] in [0,1] -> u8 labels [B,S/f,S/f] (512^2 for S = self.size; 12-region ids by default)."""
         x = self.preprocess_tensor(im01)
+        hw = (x.shape[1], x.shape[2])
         lut = None
         if convert_to_seg12:
             if self._lut12 is None or self._lut12.device != x.device:
                 self._lut12 = torch.from_numpy(SEG19_TO_SEG12.copy()).to(x.device)
             lut = self._lut12
-        return self.seg.labels(x, (512, 512), lut)
+        return self.seg.labels(x, hw, lut)
 
     @torch.no_grad()
     def forward(self, img):
         """PIL image -> [512,512] int64 label map of 19-class ids on the device (face_parsing_demo.py:162-176)."""
         x = self.preprocess_img(img)
-        return self.seg.labels(x, (512, 512), None)[0].long()
+        return self.seg.labels(x, (x.shape[1], x.shape[2]), None)[0].long()
 
 
 def init_faceParsing_pretrained_model(ckpt_path):

@@ -123,6 +123,7 @@ class BiSeNet(nn.Module):
         self.conv_out = BiSeNetOutput(256, 256, n_classes)
         self.conv_out16 = BiSeNetOutput(128, 64, n_classes)
         self.conv_out32 = BiSeNetOutput(128, 64, n_classes)
+        E.install_pack_invalidation(self)
 
     def run_main(self, x: View):
         """-> (main-head logits NHWC at 1/8 resolution, feat_cp8 view, feat_cp16 view)."""

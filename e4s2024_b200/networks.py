@@ -69,6 +69,7 @@ class Net3(nn.Module):
         for p in self.parameters():          # inference drop-in: nothing here trains
             p.requires_grad = False
         self._bias_cache = None
+        E.install_pack_invalidation(self)
 
     # ---- encoder --------------------------------------------------------------------------------
     def _encode(self, img, mask):

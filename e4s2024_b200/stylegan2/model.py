@@ -390,6 +390,7 @@ class Generator(nn.Module):
             self.to_rgbs.append(ToRGB(out_channel, style_dim, mask_op=not (rl != 17 and i >= (2 + rl // 2))))
             in_channel = out_channel
         self.n_latent = self.log_size * 2 - 2
+        E.install_pack_invalidation(self)
 
     def _region_job_keys(self):
         """(hout, wout, up2) of the masked StyledConv layers whose geometry the halo kernel takes."""

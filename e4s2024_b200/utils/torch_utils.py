@@ -8,10 +8,9 @@ from .. import _lib as L
 
 def labelMap2OneHot(label, num_cls):
     """[bs,1,H,W] integer label map -> one-hot float [bs,num_cls,H,W] (torch_utils.py:207-213)."""
-    if label.is_cuda:
-        return L.labels_to_onehot(label[:, 0].to(torch.uint8).contiguous(), num_cls)
-    bs, _, h, w = label.size()
-    return torch.zeros(bs, num_cls, h, w).scatter_(1, label.long(), 1.0)
+    if label.numel() and (int(label.min()) < 0 or int(label.max()) >= num_cls):       # scatter_ raises here in the reference
+        raise L.E4SError(f"labelMap2OneHot: labels must lie in [0, {num_cls})")
+    return L.labels_to_onehot(label[:, 0].to(torch.uint8).contiguous(), num_cls)             # CUDA only: no CPU fallback
 
 
 def tensor2im(var, is_zero_center: bool = True):

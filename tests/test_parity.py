@@ -310,3 +310,24 @@ def test_ops_autograd(dev):
         ref = torch.where(yr.detach() > 0, 1.0, 0.2) * 2 ** 0.5 * (vx.cpu() + vb.cpu().reshape(1, -1, 1, 1))
         assert maxdiff(gg, ref) < 1e-6
 
+
+
+def test_pack_cache_invalidation():
+    """Packed-weight caches are keyed on (data_ptr, _version): `.data` writes (Ranger / EMA in the reference's training code) need
+    engine.invalidate_packs, load_state_dict invalidates by itself."""
+    from e4s2024_b200 import engine as E
+    from e4s2024_b200.stylegan2.model import Generator
+    with cpu_emul.emulated():
+        G = load(Generator(32, 512, 2, remaining_layer_idx=18), 3, "emul").requires_grad_(False)
+        latent = synth.randn("inval.latent", (1, 2, G.n_latent, 512), 3)
+        mask = synth.onehot(synth.blocky_labels(1, 2, 32, cells=4, seed=3), 2)
+        run = lambda: G([latent], None, mask, input_is_latent=True, randomize_noise=False)[0]
+        a = run()
+        sd = {k: v.clone() for k, v in G.state_dict().items()}
+        G.convs[1].conv.weight.data[0, :, :, 1, 1].mul_(-1.0)   # does not bump _version
+        stale = run()
+        E.invalidate_packs(G)
+        b = run()
+        assert maxdiff(stale, a) == 0.0 and maxdiff(b, a) > 1e-3
+        G.load_state_dict(sd)                                   # the post hook drops the caches
+        assert maxdiff(run(), a) == 0.0

@@ -45,3 +45,19 @@ def test_region_jobs_match_gather_and_oracle(up):
     d_g = float((y_g.cpu() - ref).abs().max())
     print(f"up={up}: region-job path vs oracle {d_rj:.3e}, gather path vs oracle {d_g:.3e}, jobs {ctx.region_jobs[key].count} / tiles {ctx.region_jobs[key].tiles}")
     assert d_rj < 5e-4 and d_g < 5e-4
+
+
+def test_masked_mean_19_regions_vs_oracle():
+    """get_per_comp_styleCode with more regions than one launch holds (the seg19 UI variant of the reference, run_UI_seg19.py):
+    regions are processed 16 per launch; empty regions give zero vectors."""
+    from e4s2024_b200 import _lib as L
+    from oracle import e4s_oracle as orc
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn(2, 40, 16, 16, generator=g)
+    lab = torch.randint(0, 18, (2, 1, 64, 64), generator=g)            # region 18 stays empty
+    mask = torch.zeros(2, 19, 64, 64).scatter_(1, lab, 1.0)
+    codes = torch.full((2, 19, 48), 7.0, device="cuda")
+    L.masked_mean(feat.permute(0, 2, 3, 1).contiguous().cuda(), 40, mask.cuda(), codes, 8)
+    ref = orc.masked_region_mean(feat, mask)
+    assert float((codes[:, :, 8:].cpu() - ref).abs().max()) < 1e-6
+    assert float(codes[:, 18, 8:].abs().max()) == 0.0 and float((codes[:, :, :8] - 7.0).abs().max()) == 0.0
