@@ -54,7 +54,7 @@ EXPORTS = [
     "e4s_bias_act_grad_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
-    "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
+    "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_mask_member_bits_u32", "e4s_masked_mean_ws_bytes", "e4s_masked_mean_bits_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
     "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_im2tensor_f32", "e4s_morphology_f32",
 ]
@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         _lib.e4s_launch_count.restype = C.c_int64
         _lib.e4s_chan_stats_ws_bytes.restype = C.c_int64
         _lib.e4s_pack_weights_tc_bytes.restype = C.c_int64
+        _lib.e4s_masked_mean_ws_bytes.restype = C.c_int64
         if _lib.e4s_sizeof_conv() != C.sizeof(E4SConv):
             raise E4SError(f"struct E4SConv mismatch: C {_lib.e4s_sizeof_conv()} vs ctypes {C.sizeof(E4SConv)}")
     return _lib
@@ -389,6 +390,30 @@ def masked_mean(feat_nhwc, c, mask, codes, c_off):
     _check(lib().e4s_masked_mean_f32(_fp(feat_nhwc.data_ptr()), C.c_int64(pitch), b, h, w, c, _fp(mask.data_ptr()), k, mh, mw,
                                      _fp(codes.data_ptr()), C.c_int64(codes.stride(0)), C.c_int64(codes.stride(1)), c_off,
                                      _stream()), "e4s_masked_mean_f32")
+
+
+def mask_member_bits(mask: torch.Tensor) -> torch.Tensor:
+    """mask [B,K,H,W] float (K <= 32) -> int32 [B,H,W]: bit j set where mask[b,j] != 0 (region membership)."""
+    _req(mask)
+    b, k, h, w = mask.shape
+    bits = torch.empty(b, h, w, device=mask.device, dtype=torch.int32)
+    _check(lib().e4s_mask_member_bits_u32(_fp(mask.data_ptr()), b, k, h, w, _fp(bits.data_ptr()), _stream()), "e4s_mask_member_bits_u32")
+    return bits
+
+
+def masked_mean_bits(feat_nhwc, c, bits, k, codes, c_off):
+    """codes[:, :, c_off:c_off+c] = per-region mean of feat over the pixels whose membership word has the region's bit set."""
+    b, h, w, pitch = feat_nhwc.shape
+    _, mh, mw = bits.shape
+    n = int(lib().e4s_masked_mean_ws_bytes(b, c, k))
+    key = ("mm", feat_nhwc.device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 20), dtype=torch.uint8, device=feat_nhwc.device)
+        _ws_cache[key] = ws
+    _check(lib().e4s_masked_mean_bits_f32(_fp(feat_nhwc.data_ptr()), C.c_int64(pitch), b, h, w, c, _fp(bits.data_ptr()), k, mh, mw,
+                                          _fp(codes.data_ptr()), C.c_int64(codes.stride(0)), C.c_int64(codes.stride(1)), c_off,
+                                          _fp(ws.data_ptr()), _stream()), "e4s_masked_mean_bits_f32")
 
 
 def resize_bilinear_nchw_to_nhwc(x, hout, wout, c_pad, align_corners=False):

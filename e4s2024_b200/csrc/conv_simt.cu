@@ -262,6 +262,83 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_batched_kernel(const __gri
   conv_igemm_f32_body<BN>(p, m_total, blockIdx.x, blockIdx.y, 0);
 }
 
+// ---- skinny batched linear: y[r, :] = act(scale * (W^T x[r, :]) + shift) for FEW rows against LARGE weight matrices ----------------
+// The 12 LocalMLPs (1280 -> 512 -> 6656, reference models/networks.py:23-49) see one row per face: 195 MB of weights against
+// 16 rows.  In the 128-row tiles of conv_igemm_f32 that is 0.6 ms per forward (weight reads at 0.3 TB/s); here every CTA streams a
+// 128-column slab of W once with float4 loads, K split over the 8 warps (fixed-order shared-memory reduction: deterministic and
+// independent of how many rows ride along), 16 rows per pass.  Which kernel a layer takes depends on its (K, N) only, never on the
+// row count, so a sample's result does not depend on the batch it is in.
+constexpr int SK_ROWS = 16, SK_COLS = 128, SK_WARPS = 8;
+
+__device__ __forceinline__ float sk_act(float v, int act, float slope, float gain) {
+  if (act == E4S_ACT_LRELU) return (v < 0.f ? v * slope : v) * gain;
+  if (act == E4S_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == E4S_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  if (act == E4S_ACT_RSQRT_EPS) return rsqrtf(v + slope);
+  return v;
+}
+
+__global__ void __launch_bounds__(32 * SK_WARPS) linear_skinny_batched_kernel(const __grid_constant__ ConvBatch batch) {
+  const E4SConv& p = batch.c[blockIdx.z];
+  const int rows = p.batch, K = p.cin;
+  const int r0 = blockIdx.y * SK_ROWS, c0 = blockIdx.x * SK_COLS;
+  if (r0 >= rows || c0 >= p.cout_pad) return;
+  __shared__ float red[SK_ROWS][SK_COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = c0 + 4 * lane;
+  const bool col_ok = col < p.cout_pad;                       // cout_pad % 4 == 0: whole float4 groups
+  const int kper = (K + SK_WARPS - 1) / SK_WARPS;
+  const int k_lo = warp * kper, k_hi = min(K, k_lo + kper);
+  float4 acc[SK_ROWS];
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nr = min(SK_ROWS, rows - r0);
+  const float* xb = p.x + (int64_t)r0 * p.x_pitch;
+  if (col_ok) {
+#pragma unroll 4
+    for (int k = k_lo; k < k_hi; ++k) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)k * p.cout_pad + col));
+#pragma unroll
+      for (int r = 0; r < SK_ROWS; ++r) {
+        float xv = r < nr ? __ldg(xb + (int64_t)r * p.x_pitch + k) : 0.f;     // warp-uniform address: one broadcast load
+        if (p.in_square) xv *= xv;
+        acc[r].x = fmaf(xv, wv.x, acc[r].x); acc[r].y = fmaf(xv, wv.y, acc[r].y);
+        acc[r].z = fmaf(xv, wv.z, acc[r].z); acc[r].w = fmaf(xv, wv.w, acc[r].w);
+      }
+    }
+  }
+  for (int w = 0; w < SK_WARPS; ++w) {                        // warps add their K slices in index order
+    if (warp == w) {
+#pragma unroll
+      for (int r = 0; r < SK_ROWS; ++r) {
+        float4* d = reinterpret_cast<float4*>(&red[r][4 * lane]);
+        if (w == 0) *d = acc[r];
+        else {
+          float4 o = *d;
+          o.x += acc[r].x; o.y += acc[r].y; o.z += acc[r].z; o.w += acc[r].w;
+          *d = o;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < nr * SK_COLS; i += 32 * SK_WARPS) {
+    const int r = i / SK_COLS, c = i - r * SK_COLS, n = c0 + c;
+    if (n >= p.cout) continue;
+    float v = red[r][c];
+    if (p.ch_scale) v *= __ldg(p.ch_scale + n);
+    if (p.ch_shift) v += __ldg(p.ch_shift + n);
+    p.out[(int64_t)(r0 + r) * p.out_pitch + n] = sk_act(v, p.act, p.act_slope, p.act_gain);
+  }
+}
+
+// a "rows" problem (linear layer on [rows, K] vectors) whose weight matrix is large enough that streaming it dominates
+static bool skinny_problem(const E4SConv& p) {
+  return p.mode == E4S_CONV_NORMAL && p.kh == 1 && p.kw == 1 && p.hin == 1 && p.win == 1 && p.stride == 1 && p.pad == 0 && p.in_shift == 0 &&
+         !p.in_mean && !p.smod && !p.demod && !p.labels && !p.pixw && !p.noise && !p.res && !p.accumulate && p.act != E4S_ACT_PRELU &&
+         (int64_t)p.cin * p.cout >= 512 * 1024;
+}
+
 int validate_conv(const E4SConv* p) {
   E4S_REQUIRE(p != nullptr, "conv: null params");
   E4S_REQUIRE(p->x && p->w && (p->out || p->rgb), "conv: null x/w/out");
@@ -322,7 +399,8 @@ extern "C" int e4s_conv_f32_batched(const E4SConv* params, int count, void* stre
     const int n = count - base < CONV_BATCH_MAX ? count - base : CONV_BATCH_MAX;
     ConvBatch batch;
     int64_t max_mt = 1;
-    int max_cout = 1;
+    int max_cout = 1, max_rows = 1;
+    bool skinny = true;
     for (int i = 0; i < n; ++i) {
       int rc = validate_conv(&params[base + i]);
       if (rc) return rc;
@@ -331,8 +409,17 @@ extern "C" int e4s_conv_f32_batched(const E4SConv* params, int count, void* stre
       const int64_t mt = ceil_div64((int64_t)params[base + i].batch * params[base + i].hout * params[base + i].wout, BM);
       if (mt > max_mt) max_mt = mt;
       if (params[base + i].cout > max_cout) max_cout = params[base + i].cout;
+      if (params[base + i].batch > max_rows) max_rows = params[base + i].batch;
+      skinny = skinny && skinny_problem(params[base + i]);
     }
     E4S_REQUIRE(max_mt <= 0x7fffffff, "conv_f32_batched: too many tiles");
+    if (skinny) {                                              // decided by the layers' (K, N) only: batch-invariant results
+      dim3 grid((unsigned)ceil_div(max_cout, SK_COLS), (unsigned)ceil_div(max_rows, SK_ROWS), (unsigned)n);
+      linear_skinny_batched_kernel<<<grid, 32 * SK_WARPS, 0, s>>>(batch);
+      int rc = check_launch("e4s_conv_f32_batched(skinny)");
+      if (rc) return rc;
+      continue;
+    }
     dim3 grid((unsigned)max_mt, (unsigned)ceil_div(max_cout, 128), (unsigned)n);
     conv_igemm_f32_batched_kernel<128><<<grid, 256, 0, s>>>(batch);
     int rc = check_launch("e4s_conv_f32_batched");

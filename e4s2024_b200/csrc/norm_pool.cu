@@ -215,6 +215,106 @@ __global__ void __launch_bounds__(32 * MM_PY) masked_mean_kernel(const float* __
   }
 }
 
+// ---- per-region masked mean through a region-membership bit map -------------------------------------------------------------
+// The encoder pools three feature maps (64^2, 32^2, 16^2) with the same 512^2 mask.  Reading K float planes per feature pixel made
+// masked_mean_kernel a chain of L2 round trips (0.58 ms at 64^2 x 256 channels, 1.8 % of the copy bandwidth).  Here the mask is
+// reduced ONCE per forward to a u32 membership map (bit j set <=> mask[b,j,y,x] != 0: psp_encoders.py:363 tests `mask != 0`-style
+// membership, so soft / overlapping masks keep their exact semantics) and every pooling call reads one word per pixel; pixels are
+// split into MMB_SPLIT chunks per (sample, 32-channel slab) with fp64 partials reduced in a fixed order (batch-invariant).
+__global__ void __launch_bounds__(256) mask_member_bits_kernel(const float* __restrict__ mask, int k, int64_t hw, uint32_t* __restrict__ bits,
+                                                               int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / hw, p = i - b * hw;
+    const float* m = mask + b * k * hw + p;
+    uint32_t v = 0;
+    for (int j = 0; j < k; ++j) v |= (__ldg(m + (int64_t)j * hw) != 0.f ? 1u : 0u) << j;
+    bits[i] = v;
+  }
+}
+
+constexpr int MMB_SPLIT = 8;       // pixel chunks per (sample, channel slab)
+constexpr int MMB_MAXK = 32;
+
+// partial: grid (c/32, MMB_SPLIT, batch), 256 threads = 8 pixel lanes x 32 channels; ws_sum [b][slab][chunk][k][32] doubles, ws_cnt ints
+template <int KU>
+__global__ void __launch_bounds__(256) masked_mean_bits_partial_kernel(const float* __restrict__ feat, int64_t f_pitch, int h, int w, int c,
+                                                                       const uint32_t* __restrict__ bits, int k, int mh, int mw,
+                                                                       double* __restrict__ ws_sum, int* __restrict__ ws_cnt) {
+  __shared__ double red[8][32];
+  __shared__ int redc[8];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int slab = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+  const int ch = slab * 32 + cx;
+  const int hw = h * w;
+  const int per = (hw + MMB_SPLIT - 1) / MMB_SPLIT;
+  const int p_lo = chunk * per, p_hi = min(hw, p_lo + per);
+  double acc[KU];
+  int cnt[KU];
+#pragma unroll
+  for (int j = 0; j < KU; ++j) {
+    acc[j] = 0.0;
+    cnt[j] = 0;
+  }
+  const uint32_t* bb = bits + (int64_t)b * mh * mw;
+  for (int p = p_lo + py; p < p_hi; p += 16) {          // two pixels per step, loads first
+    const int p1 = p + 8;
+    const bool has1 = p1 < p_hi;
+    const int y0 = p / w, x0 = p - y0 * w;
+    const int y1 = has1 ? p1 / w : y0, x1 = has1 ? p1 - y1 * w : x0;
+    const uint32_t m0 = __ldg(bb + (int64_t)nearest_src(y0, mh, h) * mw + nearest_src(x0, mw, w));
+    const uint32_t m1 = has1 ? __ldg(bb + (int64_t)nearest_src(y1, mh, h) * mw + nearest_src(x1, mw, w)) : 0u;
+    const float v0 = ch < c ? __ldg(feat + ((int64_t)b * hw + p) * f_pitch + ch) : 0.f;
+    const float v1 = (ch < c && has1) ? __ldg(feat + ((int64_t)b * hw + p1) * f_pitch + ch) : 0.f;
+#pragma unroll
+    for (int j = 0; j < KU; ++j) {
+      const bool in0 = (m0 >> j) & 1u, in1 = (m1 >> j) & 1u;
+      acc[j] += in0 ? (double)v0 : 0.0;
+      acc[j] += in1 ? (double)v1 : 0.0;
+      cnt[j] += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+    }
+  }
+  const int64_t base = (((int64_t)b * gridDim.x + slab) * MMB_SPLIT + chunk) * k;
+#pragma unroll
+  for (int j = 0; j < KU; ++j) {
+    if (j >= k) break;
+    __syncthreads();
+    red[py][cx] = acc[j];
+    if (cx == 0) redc[py] = cnt[j];
+    __syncthreads();
+    if (py == 0) {
+      double s = 0.0;
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s += red[i][cx];
+        n += redc[i];
+      }
+      ws_sum[(base + j) * 32 + cx] = s;
+      if (cx == 0) ws_cnt[base + j] = n;
+    }
+  }
+}
+
+// final: one thread per (b, region, channel): chunks summed in index order
+__global__ void __launch_bounds__(256) masked_mean_bits_final_kernel(const double* __restrict__ ws_sum, const int* __restrict__ ws_cnt, int c, int k,
+                                                                     int slabs, float* __restrict__ codes, int64_t sb, int64_t sk, int c_off,
+                                                                     int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const int j = (int)((i / c) % k);
+    const int b = (int)(i / ((int64_t)c * k));
+    const int slab = ch >> 5, cx = ch & 31;
+    double s = 0.0;
+    int n = 0;
+    for (int q = 0; q < MMB_SPLIT; ++q) {
+      const int64_t base = (((int64_t)b * slabs + slab) * MMB_SPLIT + q) * k + j;
+      s += ws_sum[base * 32 + cx];
+      n += ws_cnt[base];
+    }
+    codes[(int64_t)b * sb + (int64_t)j * sk + c_off + ch] = n > 0 ? (float)(s / n) : 0.f;
+  }
+}
+
 __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int h, int w, int c, int ho, int wo, float* __restrict__ y,
                                     int64_t total4) {
   const int c4 = c >> 2;
@@ -310,6 +410,41 @@ extern "C" int e4s_masked_mean_f32(const float* feat, int64_t f_pitch, int batch
     rc = check_launch("masked_mean");
   }
   return rc;
+}
+
+extern "C" int e4s_mask_member_bits_u32(const float* mask, int batch, int k, int h, int w, uint32_t* bits, void* stream) {
+  E4S_REQUIRE(mask && bits && batch > 0 && k > 0 && k <= MMB_MAXK && h > 0 && w > 0, "mask_member_bits: bad args (k must be in 1..32)");
+  const int64_t hw = (int64_t)h * w, total = (int64_t)batch * hw;
+  mask_member_bits_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(mask, k, hw, bits, total);
+  return check_launch("mask_member_bits");
+}
+
+extern "C" int64_t e4s_masked_mean_ws_bytes(int batch, int c, int k) {
+  const int64_t n = (int64_t)batch * ceil_div(c, 32) * MMB_SPLIT * k;
+  return n * 32 * (int64_t)sizeof(double) + n * (int64_t)sizeof(int) + 256;
+}
+
+extern "C" int e4s_masked_mean_bits_f32(const float* feat, int64_t f_pitch, int batch, int h, int w, int c, const uint32_t* bits, int k,
+                                        int mh, int mw, float* codes, int64_t codes_stride_b, int64_t codes_stride_k, int c_off, void* ws,
+                                        void* stream) {
+  E4S_REQUIRE(feat && bits && codes && ws && batch > 0 && h > 0 && w > 0 && c > 0, "masked_mean_bits: bad args");
+  E4S_REQUIRE(k > 0 && k <= MMB_MAXK && mh > 0 && mw > 0, "masked_mean_bits: k must be in 1..%d", MMB_MAXK);
+  E4S_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "masked_mean_bits: workspace must be 16-byte aligned");
+  const int slabs = ceil_div(c, 32);
+  const int64_t n = (int64_t)batch * slabs * MMB_SPLIT * k;
+  double* ws_sum = static_cast<double*>(ws);
+  int* ws_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + ((n * 32 * (int64_t)sizeof(double) + 15) & ~(int64_t)15));
+  dim3 grid(slabs, MMB_SPLIT, batch);
+  if (k <= 16)
+    masked_mean_bits_partial_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, bits, k, mh, mw, ws_sum, ws_cnt);
+  else
+    masked_mean_bits_partial_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(feat, f_pitch, h, w, c, bits, k, mh, mw, ws_sum, ws_cnt);
+  int rc = check_launch("masked_mean_bits_partial");
+  if (rc) return rc;
+  const int64_t total = (int64_t)batch * k * c;
+  masked_mean_bits_final_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ws_sum, ws_cnt, c, k, slabs, codes, codes_stride_b,
+                                                                                    codes_stride_k, c_off, total);
+  return check_launch("masked_mean_bits_final");
 }
 
 extern "C" int e4s_maxpool3x3s2_nhwc_f32(const float* x, int batch, int h, int w, int c, float* y, void* stream) {

@@ -44,12 +44,18 @@ class FSEncoder_PSP(nn.Module):
         st = L.chan_stats(c0.t, 64)
         cur = View(L.residual_combine(c0.t, 64, a_stats=st, prelu=self.input_layer[2].weight.detach()))
         seg = segmap.contiguous().float()
-        codes = torch.empty(b, seg.shape[1], 256 + 512 + 512, device=x.t.device, dtype=torch.float32)
+        k = seg.shape[1]
+        codes = torch.empty(b, k, 256 + 512 + 512, device=x.t.device, dtype=torch.float32)
         off = {6: 0, 20: 256, 23: 768}
+        # the three poolings share the mask: reduce it once to a region-membership bit map (K <= 32), one word per pixel
+        bits = L.mask_member_bits(seg) if k <= 32 else None
         for i, unit in enumerate(self.body):
             cur = unit.run(cur)
             if i in off:
-                L.masked_mean(cur.t, cur.c, seg, codes, off[i])
+                if bits is not None:
+                    L.masked_mean_bits(cur.t, cur.c, bits, k, codes, off[i])
+                else:
+                    L.masked_mean(cur.t, cur.c, seg, codes, off[i])
         _, h, w = cur.bhw
         structure_feats = torch.zeros(b, cur.c, h, w, device=x.t.device, dtype=torch.float32)
         return codes, structure_feats

@@ -225,6 +225,14 @@ int e4s_masked_mean_f32(const float* feat, int64_t f_pitch, int batch, int h, in
                         int mh, int mw, float* codes, int64_t codes_stride_b, int64_t codes_stride_k, int c_off,
                         void* stream);
 
+/* The same pooling for several feature maps of one forward: the mask is reduced once to a membership map, bits[b,y,x] bit j set <=>
+ * mask[b,j,y,x] != 0 (k <= 32), and each call reads one word per feature pixel.  ws: e4s_masked_mean_ws_bytes(batch, c, k) bytes
+ * (fp64 partial sums of 8 pixel chunks, reduced in a fixed order: batch-invariant results). */
+int e4s_mask_member_bits_u32(const float* mask, int batch, int k, int h, int w, uint32_t* bits, void* stream);
+int64_t e4s_masked_mean_ws_bytes(int batch, int c, int k);
+int e4s_masked_mean_bits_f32(const float* feat, int64_t f_pitch, int batch, int h, int w, int c, const uint32_t* bits, int k, int mh,
+                             int mw, float* codes, int64_t codes_stride_b, int64_t codes_stride_k, int c_off, void* ws, void* stream);
+
 /* bilinear resize NCHW -> NHWC (c_pad channels, zero filled) or NHWC->NCHW; align_corners as torch */
 int e4s_resize_bilinear_nchw_to_nhwc_f32(const float* x, int batch, int c, int hin, int win, float* y, int hout,
                                          int wout, int c_pad, int align_corners, void* stream);

@@ -373,6 +373,19 @@ def masked_mean(feat, c, mask, codes, c_off):
     codes[:, :, c_off:c_off + c] = torch.where(area[..., None] > 0, tot / area.clamp(min=1)[..., None], torch.zeros_like(tot)).float()
 
 
+def mask_member_bits(mask):
+    k = mask.shape[1]
+    w = (2 ** torch.arange(k, dtype=torch.int64)).view(1, k, 1, 1)
+    v = ((mask != 0).to(torch.int64) * w).sum(1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+
+
+def masked_mean_bits(feat, c, bits, k, codes, c_off):
+    v = bits.to(torch.int64) & 0xFFFFFFFF
+    mask = torch.stack([((v >> j) & 1).float() for j in range(k)], dim=1)
+    masked_mean(feat, c, mask, codes, c_off)
+
+
 def resize_bilinear_nchw_to_nhwc(x, hout, wout, c_pad, align_corners=False):
     y = F.interpolate(x, (hout, wout), mode="bilinear", align_corners=align_corners)
     return nchw_to_nhwc(y, c_pad)
@@ -402,7 +415,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
 
 
 _NAMES = ["conv", "conv_batched", "pack_weights_tc", "pack_conv_weights", "pack_upconv_weights", "upfirdn2d", "upfirdn2d_general", "bias_act", "bias_act_grad", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
-          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "im2tensor", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean",
+          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "im2tensor", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean", "mask_member_bits", "masked_mean_bits",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
 

@@ -61,3 +61,47 @@ def test_masked_mean_19_regions_vs_oracle():
     ref = orc.masked_region_mean(feat, mask)
     assert float((codes[:, :, 8:].cpu() - ref).abs().max()) < 1e-6
     assert float(codes[:, 18, 8:].abs().max()) == 0.0 and float((codes[:, :, :8] - 7.0).abs().max()) == 0.0
+
+
+def test_masked_mean_bits_matches_plane_kernel_and_oracle():
+    """The membership-bit-map pooling the encoder uses (one word per pixel, 8 pixel chunks) against the float-plane kernel and the
+    oracle, with an OVERLAPPING soft mask (a pixel in two regions counts for both, like `mask != 0` in the reference)."""
+    from e4s2024_b200 import _lib as L
+    from oracle import e4s_oracle as orc
+    g = torch.Generator().manual_seed(11)
+    for (c, hw, k) in ((256, 64, 12), (40, 16, 19), (512, 32, 12)):
+        feat = torch.randn(2, c, hw, hw, generator=g)
+        lab = torch.randint(0, k - 1, (2, 1, 128, 128), generator=g)
+        mask = torch.zeros(2, k, 128, 128).scatter_(1, lab, 1.0)
+        mask[:, 1, 10:60, 20:90] = 0.3                                  # overlaps whatever is there
+        fn = feat.permute(0, 2, 3, 1).contiguous().cuda()
+        a = torch.zeros(2, k, c + 8, device="cuda")
+        L.masked_mean_bits(fn, c, L.mask_member_bits(mask.cuda()), k, a, 8)
+        ref = orc.masked_region_mean(feat, mask)
+        assert float((a[:, :, 8:].cpu() - ref).abs().max()) < 1e-6
+        b = torch.zeros(2, k, c + 8, device="cuda")
+        L.masked_mean(fn, c, mask.cuda(), b, 8)
+        assert float((a - b).abs().max()) < 1e-6
+        solo = torch.zeros(1, k, c + 8, device="cuda")
+        L.masked_mean_bits(fn[1:].contiguous(), c, L.mask_member_bits(mask[1:].cuda()), k, solo, 8)
+        assert torch.equal(solo[0], a[1])                               # batch-invariant
+
+
+def test_skinny_batched_linear_matches_fp64_and_is_batch_invariant():
+    """The LocalMLP-shaped batched launch (few rows, large weights -> linear_skinny_batched_kernel) against torch fp64, for row counts
+    on both sides of its 16-row pass, with the in_square / rsqrt form of the demodulation GEMM and a leaky-ReLU epilogue."""
+    from e4s2024_b200 import _lib as L, engine as E
+    g = torch.Generator().manual_seed(12)
+    w = torch.randn(1040, 1280, generator=g) / 36.0
+    bias = torch.randn(1040, generator=g)
+    pw = E.pack_linear_weight(w.cuda())
+    assert pw.cin * pw.cout >= 512 * 1024
+    outs = {}
+    for rows in (1, 16, 37):
+        x = torch.randn(40, 1280, generator=torch.Generator().manual_seed(13))[:rows].contiguous()
+        y, p = E.linear_rows(x.cuda(), rows, 1280, 0, pw, bias=bias.cuda(), act=L.ACT_LRELU, slope=0.01, gain=1.0, launch=False)
+        L.conv_batched([p])
+        ref = torch.nn.functional.leaky_relu(x.double() @ w.double().t() + bias.double(), 0.01)
+        assert float((y.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        outs[rows] = y.cpu()
+    assert torch.equal(outs[1][0], outs[16][0]) and torch.equal(outs[16][5], outs[37][5])
