@@ -56,7 +56,7 @@ EXPORTS = [
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_mask_member_bits_u32", "e4s_masked_mean_ws_bytes", "e4s_masked_mean_bits_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
-    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_im2tensor_f32", "e4s_morphology_f32",
+    "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_im2tensor_f32", "e4s_morphology_f32", "e4s_depthwise_conv_f32", "e4s_soft_erosion_finish_f32", "e4s_pyr_down_f32", "e4s_pyr_up_f32", "e4s_pyr_blend_f32",
 ]
 
 _lib = None
@@ -313,6 +313,56 @@ def morphology(x: torch.Tensor, neighborhood: torch.Tensor, origin, border_value
     out = torch.empty_like(x)
     _check(lib().e4s_morphology_f32(_fp(x.data_ptr()), _fp(neighborhood.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w, se_h, se_w,
                                     int(origin[0]), int(origin[1]), C.c_float(border_value), int(dilate), _stream()), "e4s_morphology_f32")
+    return out
+
+
+def depthwise_conv(x: torch.Tensor, weight: torch.Tensor, min_with_input: bool = False) -> torch.Tensor:
+    """x [B,C,H,W], weight [k,k] (odd k): depthwise correlation with zero padding k//2 (optionally min(x, conv(x)))."""
+    _req(x), _req(weight)
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    _check(lib().e4s_depthwise_conv_f32(_fp(x.data_ptr()), _fp(weight.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w, weight.shape[0],
+                                        int(min_with_input), _stream()), "e4s_depthwise_conv_f32")
+    return out
+
+
+def soft_erosion_finish(x: torch.Tensor, threshold: float):
+    """in place on x [..] fp32 -> (x, mask bool): x >= thr -> 1, else x / max(x below thr)."""
+    _req(x)
+    mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    scratch = torch.empty(1, device=x.device, dtype=torch.float32)
+    _check(lib().e4s_soft_erosion_finish_f32(_fp(x.data_ptr()), _fp(mask.data_ptr()), C.c_int64(x.numel()), _f32(threshold), _fp(scratch.data_ptr()),
+                                             _stream()), "e4s_soft_erosion_finish_f32")
+    return x, mask.bool()
+
+
+def pyr_down(x: torch.Tensor, round_u8: bool = False) -> torch.Tensor:
+    _req(x)
+    b, c, h, w = x.shape
+    out = torch.empty(b, c, (h + 1) // 2, (w + 1) // 2, device=x.device, dtype=torch.float32)
+    _check(lib().e4s_pyr_down_f32(_fp(x.data_ptr()), _fp(out.data_ptr()), C.c_int64(b * c), h, w, int(round_u8), _stream()), "e4s_pyr_down_f32")
+    return out
+
+
+def pyr_up(x: torch.Tensor, other: Optional[torch.Tensor] = None, mode: int = 0) -> torch.Tensor:
+    """mode 0: up(x); 1: other - up(x); 2: up(x) + other.  other [B,C,2H,2W]."""
+    _req(x)
+    b, c, h, w = x.shape
+    if other is not None:
+        _req(other)
+        if tuple(other.shape) != (b, c, 2 * h, 2 * w):
+            raise E4SError(f"pyr_up: other must be {(b, c, 2 * h, 2 * w)}, got {tuple(other.shape)}")
+    out = torch.empty(b, c, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
+    _check(lib().e4s_pyr_up_f32(_fp(x.data_ptr()), _fp(_p(other)), _fp(out.data_ptr()), C.c_int64(b * c), h, w, mode, _stream()), "e4s_pyr_up_f32")
+    return out
+
+
+def pyr_blend(la: torch.Tensor, lb: torch.Tensor, gm: torch.Tensor) -> torch.Tensor:
+    _req(la), _req(lb), _req(gm)
+    b, c, h, w = la.shape
+    out = torch.empty_like(la)
+    _check(lib().e4s_pyr_blend_f32(_fp(la.data_ptr()), _fp(lb.data_ptr()), _fp(gm.data_ptr()), _fp(out.data_ptr()), b, c, gm.shape[1], h, w, _stream()),
+           "e4s_pyr_blend_f32")
     return out
 
 

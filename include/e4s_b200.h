@@ -277,6 +277,23 @@ int e4s_im2tensor_f32(const uint8_t* x, float* y01, float* ynorm, int batch, int
 int e4s_morphology_f32(const float* x, const float* neighborhood, float* out, int64_t planes, int h, int w, int se_h, int se_w,
                        int origin_y, int origin_x, float border_value, int dilate, void* stream);
 
+/* ---- paste-back, NCHW fp32 planes [planes, h, w] ------------------------------------------------------------------
+ * e4s_depthwise_conv_f32: out = correlate(x, weight[k][k]) with zero padding k/2 (F.conv2d(x, w, groups=C, padding=r) of SoftErosion,
+ *   reference utils/paste_back_tricks.py:32-36); min_with_input != 0: out = min(x, conv(x)) (the iterations - 1 first passes).
+ * e4s_soft_erosion_finish_f32: in place, x >= threshold -> 1 (mask byte 1), else x / max(x below threshold) over the WHOLE tensor
+ *   (paste_back_tricks.py:38-40); scratch_max: one device float.
+ * e4s_pyr_down_f32 / e4s_pyr_up_f32: cv2.pyrDown / cv2.pyrUp arithmetic ([1 4 6 4 1] Gaussian, BORDER_REFLECT_101, output
+ *   (h+1)/2 x (w+1)/2 resp. 2h x 2w; multi_band_blending.py:17-19,30-31,47).  round_u8: cv2's uint8 form floor((sum+128)/256) on integer
+ *   pixel values.  pyr_up mode 0: out = up(x); 1: out = other - up(x) (Laplacian level); 2: out = up(x) + other (reconstruction).
+ * e4s_pyr_blend_f32: out = la*gm + lb*(1-gm) (multi_band_blending.py:40-42); gm [batch, m_channels, h, w], m_channels = channels or 1. */
+int e4s_depthwise_conv_f32(const float* x, const float* weight, float* out, int64_t planes, int h, int w, int k, int min_with_input,
+                           void* stream);
+int e4s_soft_erosion_finish_f32(float* x, uint8_t* mask, int64_t n, float threshold, float* scratch_max, void* stream);
+int e4s_pyr_down_f32(const float* x, float* out, int64_t planes, int h, int w, int round_u8, void* stream);
+int e4s_pyr_up_f32(const float* x, const float* other, float* out, int64_t planes, int h, int w, int mode, void* stream);
+int e4s_pyr_blend_f32(const float* la, const float* lb, const float* gm, float* out, int batch, int channels, int m_channels, int h, int w,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -500,3 +500,108 @@ def morphology(x: torch.Tensor, kernel: torch.Tensor, dilate: bool, structuring_
                 t = win - nb[i, j]                                       # :184-186: min(unfolded - neighborhood)
                 out = t if out is None else torch.minimum(out, t)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# paste-back: SoftErosion and the Laplacian-pyramid blend
+# --------------------------------------------------------------------------------------
+
+def soft_erosion_kernel(kernel_size: int = 15) -> torch.Tensor:
+    """utils/paste_back_tricks.py:24-30 (= gradio_utils/face_swapping.py:31-38): cone kernel max(dist) - dist, normalised."""
+    r = kernel_size // 2
+    ax = torch.arange(0., kernel_size)
+    y, x = torch.meshgrid(ax, ax, indexing="ij")
+    dist = torch.sqrt((x - r) ** 2 + (y - r) ** 2)
+    k = dist.max() - dist
+    return k / k.sum()
+
+
+def soft_erosion(x: torch.Tensor, kernel_size: int = 15, threshold: float = 0.6, iterations: int = 1):
+    """utils/paste_back_tricks.py:32-42 (SoftErosion.forward): depthwise conv (zero padding), optional min-iterations, threshold to 1,
+    the rest divided by its GLOBAL maximum.  -> (x, mask bool)."""
+    w = soft_erosion_kernel(kernel_size).to(x.device).view(1, 1, kernel_size, kernel_size).repeat(x.shape[1], 1, 1, 1)
+    x = x.float()
+    pad = kernel_size // 2
+    for _ in range(iterations - 1):
+        x = torch.min(x, F.conv2d(x, w, groups=x.shape[1], padding=pad))
+    x = F.conv2d(x, w, groups=x.shape[1], padding=pad)
+    mask = x >= threshold
+    x = x.clone()
+    x[mask] = 1.0
+    x[~mask] /= x[~mask].max()
+    return x, mask
+
+
+def _reflect101(i: int, n: int) -> int:
+    if n == 1:
+        return 0
+    while i < 0 or i >= n:
+        i = -i if i < 0 else 2 * (n - 1) - i
+    return i
+
+
+def pyr_down(a: np.ndarray, round_u8: bool = False) -> np.ndarray:
+    """cv2.pyrDown (multi_band_blending.py:17-19) for float32 HxW[xC] arrays: separable [1 4 6 4 1]/16, BORDER_REFLECT_101, even samples,
+    output ((h+1)//2, (w+1)//2).  round_u8: the uint8 form ((sum + 128) >> 8 on integer pixels), what cv2 does when the pipelines hand
+    it uint8 images.  Checked against cv2 in oracle/make_golden_r2.py."""
+    a = np.asarray(a, np.float32)
+    h, w = a.shape[:2]
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    row = np.zeros((h, ow) + a.shape[2:], np.float32)
+    for x in range(ow):
+        xs = [_reflect101(2 * x + i, w) for i in range(-2, 3)]
+        row[:, x] = a[:, xs[2]] * 6 + (a[:, xs[1]] + a[:, xs[3]]) * 4 + a[:, xs[0]] + a[:, xs[4]]
+    out = np.zeros((oh, ow) + a.shape[2:], np.float32)
+    for y in range(oh):
+        ys = [_reflect101(2 * y + i, h) for i in range(-2, 3)]
+        out[y] = row[ys[2]] * 6 + (row[ys[1]] + row[ys[3]]) * 4 + row[ys[0]] + row[ys[4]]
+    if round_u8:
+        return np.floor((out + 128.0) / 256.0).astype(np.float32)
+    return out * np.float32(1 / 256)
+
+
+def pyr_up(a: np.ndarray) -> np.ndarray:
+    """cv2.pyrUp (multi_band_blending.py:30-31,47) for float32 arrays: zero-insert x2, [1 4 6 4 1]/8 per axis; the left / top neighbour
+    of the first sample is reflected (101), the right / bottom neighbour of the last one replicated -- as OpenCV does."""
+    def up1(t, axis):
+        t = np.moveaxis(t, axis, 0)
+        n = t.shape[0]
+        out = np.zeros((2 * n,) + t.shape[1:], np.float32)
+        for x in range(n):
+            left = t[x - 1] if x > 0 else t[min(1, n - 1)]
+            right = t[x + 1] if x + 1 < n else t[x]
+            out[2 * x] = left + t[x] * 6 + right
+            out[2 * x + 1] = (t[x] + right) * 4
+        return np.moveaxis(out, 0, axis)
+    return up1(up1(np.asarray(a, np.float32), 1), 0) * np.float32(1 / 64)
+
+
+def laplacian_pyramid_blend(A: np.ndarray, B: np.ndarray, m: np.ndarray, num_levels: int = 6) -> np.ndarray:
+    """swap_face_fine/multi_band_blending.py:6-49 (Laplacian_Pyramid_Blending_with_mask) on HxWxC arrays.  uint8 A / B keep cv2's
+    per-level integer rounding in their Gaussian pyramids (the pipelines pass np.array(PIL) for A)."""
+    def gauss(x):
+        u8 = np.asarray(x).dtype == np.uint8
+        g = np.asarray(x, np.float32)
+        out = [g]
+        for _ in range(num_levels):
+            g = pyr_down(g, round_u8=u8)
+            out.append(g)
+        return out
+    gpA, gpB, gpM = gauss(A), gauss(B), gauss(m)
+    lpA, lpB, gpMr = [gpA[num_levels - 1]], [gpB[num_levels - 1]], [gpM[num_levels - 1]]
+    for i in range(num_levels - 1, 0, -1):
+        lpA.append(gpA[i - 1] - pyr_up(gpA[i]))
+        lpB.append(gpB[i - 1] - pyr_up(gpB[i]))
+        gpMr.append(gpM[i - 1])
+    LS = [la * gm + lb * (1.0 - gm) for la, lb, gm in zip(lpA, lpB, gpMr)]
+    ls = LS[0]
+    for i in range(1, num_levels):
+        ls = pyr_up(ls) + LS[i]
+    return ls
+
+
+def blending(full_img: np.ndarray, ori_img: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """multi_band_blending.py:52-74 for 1024x1024 inputs (the cv2.resize calls are identities there): 10-level blend, clip, uint8."""
+    assert full_img.shape[:2] == (1024, 1024) and ori_img.shape[:2] == (1024, 1024)
+    img = laplacian_pyramid_blend(full_img, ori_img, np.float32(mask), 10)
+    return np.uint8(np.clip(img, 0, 255))

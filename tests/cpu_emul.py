@@ -270,6 +270,40 @@ def im2tensor(x, want01=True, want_norm=True, mean=(0.5, 0.5, 0.5), std=(0.5, 0.
     return (x01 if want01 else None), (xn if want_norm else None)
 
 
+def depthwise_conv(x, weight, min_with_input=False):
+    k = weight.shape[0]
+    y = torch.nn.functional.conv2d(x, weight.view(1, 1, k, k).repeat(x.shape[1], 1, 1, 1), groups=x.shape[1], padding=k // 2)
+    return torch.min(x, y) if min_with_input else y
+
+
+def soft_erosion_finish(x, threshold):
+    mask = x >= threshold
+    x[mask] = 1.0
+    x[~mask] /= x[~mask].max()
+    return x, mask
+
+
+def _per_plane(x, fn):
+    from oracle import e4s_oracle as orc  # noqa: F401
+    b, c = x.shape[:2]
+    return torch.stack([torch.stack([torch.from_numpy(fn(x[i, j].numpy())) for j in range(c)]) for i in range(b)])
+
+
+def pyr_down(x, round_u8=False):
+    from oracle import e4s_oracle as orc
+    return _per_plane(x, lambda a: orc.pyr_down(a, round_u8))
+
+
+def pyr_up(x, other=None, mode=0):
+    from oracle import e4s_oracle as orc
+    up = _per_plane(x, orc.pyr_up)
+    return up if mode == 0 else (other - up if mode == 1 else up + other)
+
+
+def pyr_blend(la, lb, gm):
+    return la * gm + lb * (1.0 - gm)
+
+
 def swap_comp_styles(target, source, comp_mask, below_face):
     """e4s_swap_comp_styles_f32 restated with torch (mode per component: target / source / average)."""
     out = target.clone()
@@ -415,7 +449,7 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
 
 
 _NAMES = ["conv", "conv_batched", "pack_weights_tc", "pack_conv_weights", "pack_upconv_weights", "upfirdn2d", "upfirdn2d_general", "bias_act", "bias_act_grad", "noise_bias_act_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
-          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "im2tensor", "morphology", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean", "mask_member_bits", "masked_mean_bits",
+          "mask_labels", "labels_to_onehot", "swap_comp_styles", "tensor2im_u8", "im2tensor", "morphology", "depthwise_conv", "soft_erosion_finish", "pyr_down", "pyr_up", "pyr_blend", "torgb", "chan_stats", "vec_fc", "residual_combine", "masked_mean", "mask_member_bits", "masked_mean_bits",
           "resize_bilinear_nchw_to_nhwc", "resize_bilinear_nhwc_to_nchw", "maxpool3x3s2", "upsample_argmax",
           "bicubic_down_norm"]
 

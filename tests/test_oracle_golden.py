@@ -152,3 +152,20 @@ def test_morphology(golden):
         close(orc.morphology(x, kw["kernel"], True, **okw), g[name + "_dil"], 0.0)
         close(orc.morphology(x, kw["kernel"], False, **okw), g[name + "_ero"], 0.0)
 
+
+
+def test_soft_erosion(golden):
+    g = golden("soft_erosion")
+    for name in ("default", "k7_it3"):
+        ks, it = [int(v) for v in g[name + "_cfg"]]
+        y, mk = orc.soft_erosion(T(g["x"]), kernel_size=ks, threshold=float(g[name + "_thr"]), iterations=it)
+        assert float((y - T(g[name + "_y"])).abs().max()) < 1e-6 and int((mk.numpy() != g[name + "_mask"]).sum()) == 0
+
+
+def test_laplacian_blend(golden):
+    g = golden("laplacian_blend")
+    lv = int(g["levels"])
+    out = orc.laplacian_pyramid_blend(g["A8"], g["B"], g["m"], lv)
+    assert float(np.abs(out - g["out_u8A"]).max()) < 1e-3                  # [0,255] scale; cv2's SIMD sums in another order
+    out = orc.laplacian_pyramid_blend(g["A8"].astype(np.float32), g["B"], g["m"], lv)
+    assert float(np.abs(out - g["out_fA"]).max()) < 1e-3

@@ -331,3 +331,40 @@ def test_pack_cache_invalidation():
         assert maxdiff(stale, a) == 0.0 and maxdiff(b, a) > 1e-3
         G.load_state_dict(sd)                                   # the post hook drops the caches
         assert maxdiff(run(), a) == 0.0
+
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_soft_erosion(golden, dev):
+    """SoftErosion (cone-kernel depthwise conv, min-iterations, threshold, global-max normalisation) vs the reference's
+    own module output; hard-mask bits may differ only where the softened value sits on the threshold."""
+    from e4s2024_b200.utils.paste_back_tricks import SoftErosion
+    g = golden("soft_erosion")
+    for name in ("default", "k7_it3"):
+        ks, it = [int(v) for v in g[name + "_cfg"]]
+        thr = float(g[name + "_thr"])
+        with ctx_for(dev):
+            mod = SoftErosion(kernel_size=ks, threshold=thr, iterations=it)
+            mod = mod.to("cpu" if dev == "emul" else "cuda")
+            y, mk = mod(to(dev, T(g["x"])))
+        assert mk.dtype == torch.bool and tuple(y.shape) == g[name + "_y"].shape
+        bad = mk.cpu().numpy() != g[name + "_mask"]
+        assert bad.sum() <= 4, int(bad.sum())
+        assert float((y.cpu() - T(g[name + "_y"])).abs()[torch.from_numpy(~bad)].max()) < 1e-5
+
+
+@pytest.mark.parametrize("dev", DEVS)
+def test_laplacian_pyramid_blend(golden, dev):
+    """the multi-band blend (cv2.pyrDown / pyrUp arithmetic) vs the reference function's output, for the uint8 target
+    frame + float composite the pipelines pass, and for all-float inputs; batched."""
+    from e4s2024_b200.multi_band_blending import Laplacian_Pyramid_Blending_with_mask
+    g = golden("laplacian_blend")
+    lv = int(g["levels"])
+    hwc = lambda a: T(a).permute(2, 0, 1)[None].contiguous()
+    with ctx_for(dev):
+        A8, Bf, m = to(dev, hwc(g["A8"]), hwc(g["B"]), hwc(g["m"]))
+        out = Laplacian_Pyramid_Blending_with_mask(A8, Bf, m, lv)
+        out_f = Laplacian_Pyramid_Blending_with_mask(A8.float(), Bf, m[:, :1], lv)          # one mask plane broadcast over channels
+        two = Laplacian_Pyramid_Blending_with_mask(torch.cat([A8, A8]), torch.cat([Bf, Bf]), torch.cat([m, m]), lv)
+    assert maxdiff(out[0].permute(1, 2, 0), g["out_u8A"]) < 1e-3
+    assert maxdiff(out_f[0].permute(1, 2, 0), g["out_fA"]) < 1e-3
+    assert maxdiff(two[1], out[0]) == 0.0
