@@ -49,8 +49,8 @@ class E4SConv(C.Structure):
 
 
 EXPORTS = [
-    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs",
-    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_pack_weights_tc_fmt", "e4s_pack_conv_weights_f32", "e4s_pack_upconv_weights_f32", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
+    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs", "e4s_upz_build_rows", "e4s_pack_convt_weights_f32", "e4s_conv_tc_upz",
+    "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_debug_upz_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_pack_weights_tc_fmt", "e4s_pack_conv_weights_f32", "e4s_pack_upconv_weights_f32", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_bias_act_grad_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
     "e4s_torgb_f32", "e4s_chan_stats_ws_bytes", "e4s_chan_stats_f32", "e4s_vec_fc_f32",
@@ -144,6 +144,32 @@ def region_tile_jobs(labels: torch.Tensor, hout: int, wout: int, up2: bool, regi
     _check(lib().e4s_region_tile_jobs(_fp(labels.data_ptr()), b, lh, lw, hout, wout, int(up2), _fp(jobs.data_ptr()),
                                       _fp(count_slot.data_ptr()), max_jobs, _stream()), "e4s_region_tile_jobs")
     return jobs
+
+
+def upz_build_rows(labels: torch.Tensor, hin: int, win: int, max_rows: int, count_slot: torch.Tensor):
+    """-> (cells int32 [B, hin+1, win+1, 2], rows int32 [max_rows, 2]); count_slot: zeroed int32[1] view that receives the row count."""
+    b, lh, lw = labels.shape
+    cells = torch.empty(b, hin + 1, win + 1, 2, dtype=torch.int32, device=labels.device)
+    rows = torch.empty(max_rows, 2, dtype=torch.int32, device=labels.device)
+    _check(lib().e4s_upz_build_rows(_fp(labels.data_ptr()), b, lh, lw, hin, win, _fp(cells.data_ptr()), _fp(rows.data_ptr()),
+                                    _fp(count_slot.data_ptr()), max_rows, _stream()), "e4s_upz_build_rows")
+    return cells, rows
+
+
+def pack_convt_weights(w: torch.Tensor, cout_pad: int, scale: float = 1.0) -> torch.Tensor:
+    """w [Co,Ci,3,3] -> [9, Ci, cout_pad] fp32: the taps of conv_transpose2d as [Ci x Co] matrices in conv_tc_upz's consumption order."""
+    _req(w)
+    co, ci = w.shape[:2]
+    out = torch.empty(9, ci, cout_pad, device=w.device, dtype=torch.float32)
+    _check(lib().e4s_pack_convt_weights_f32(_fp(w.data_ptr()), _fp(out.data_ptr()), co, ci, cout_pad, _f32(scale), _stream()),
+           "e4s_pack_convt_weights_f32")
+    return out
+
+
+def conv_upz(params: E4SConv, tc9: torch.Tensor, fir: torch.Tensor, cells: torch.Tensor, rows: torch.Tensor, count: torch.Tensor,
+             max_rows: int, z: torch.Tensor):
+    _check(lib().e4s_conv_tc_upz(C.byref(params), _fp(tc9.data_ptr()), _fp(fir.data_ptr()), _fp(cells.data_ptr()), _fp(rows.data_ptr()),
+                                 _fp(count.data_ptr()), int(max_rows), _fp(z.data_ptr()), _stream()), "e4s_conv_tc_upz")
 
 
 def conv_batched(params_list):

@@ -68,6 +68,8 @@ class PackedConv:
     kw: int
     phases: int = 1
     tc: Optional[torch.Tensor] = None
+    tc9: Optional[torch.Tensor] = None   # up-convolutions: the 9 conv_transpose taps packed for e4s_conv_tc_upz
+    fir: Optional[torch.Tensor] = None   # ... and the 4x4 blur kernel its finishing pass applies
     tc_fmt: int = L.TC_BF16          # operand format of the tensor-core image (E4SConv.tc_fmt)
     tc_out_scale: float = 1.0        # 1 / the power-of-two pre-scale of fp16 weights (E4SConv.tc_out_scale)
 
@@ -100,6 +102,16 @@ def wide_eligible(cin: int, cout: int, hin: int, win: int, up2: bool) -> bool:
 
 
 WIDE_OVER_REGION_JOBS = float(os.environ.get("E4S_WIDE_RATIO", "1.25"))
+
+
+def upz_eligible(cin: int, cout: int) -> bool:
+    """Mirror of e4s_conv_tc_upz's shape check: masked up-convolutions that can run as the (cell, region) conv_transpose GEMM."""
+    return _ENGINE == "tc" and os.environ.get("E4S_UPZ", "1") != "0" and cin % 64 == 0 and cout % 128 == 0 and tc_available()
+
+
+# run the (cell, region) form while it has at most this many rows per cell (its MMA work is rows x 9 against cells x 36 -- x72 on tiles
+# with mixed phases -- for the poly-phase kernel); beyond that the poly-phase kernel runs (device-side predicate)
+UPZ_RATIO = float(os.environ.get("E4S_UPZ_RATIO", "2.5"))
 
 
 def tc_eligible(cin: int, cout: int) -> bool:
@@ -150,8 +162,14 @@ def pack_up_weight(w: torch.Tensor, fir: torch.Tensor, want_tc: bool = True, sca
     """conv_transpose2d(stride 2, weight w[Co,Ci,3,3] used as [Ci,Co,3,3]) followed by upfirdn2d(fir 4x4, pad=(1,1)) as four 3x3
     phase filters applied at input resolution (one kernel: e4s_pack_upconv_weights_f32)."""
     co, ci = w.shape[:2]
-    m = L.pack_upconv_weights(w.detach().contiguous().float(), fir.detach().contiguous().float().to(w.device), pad_to(co, 4), scale)
-    return _finish_pack(m, ci, co, 3, 3, 4, want_tc)
+    wf, ff = w.detach().contiguous().float(), fir.detach().contiguous().float().to(w.device)
+    m = L.pack_upconv_weights(wf, ff, pad_to(co, 4), scale)
+    pc = _finish_pack(m, ci, co, 3, 3, 4, want_tc)
+    if pc.tc is not None and upz_eligible(ci, co):
+        m9 = L.pack_convt_weights(wf, pad_to(co, 4), scale)
+        pc.tc9 = L.pack_weights_tc(m9, 9, ci, ci, co, pad_to(co, 4))
+        pc.fir = ff
+    return pc
 
 
 class View:
@@ -184,7 +202,8 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
          smod=None, demod=None, labels=None, regions=1, smod_off=0, demod_off=0, pixw=None, ch_scale=None, ch_shift=None,
          noise=None, noise_w=None, res: Optional[View] = None, res_after_act=False, act=L.ACT_NONE, slope=0.0, gain=1.0,
          prelu=None, out: Optional[View] = None, accumulate=False, engine: Optional[str] = None,
-         region_jobs: Optional["RegionJobs"] = None, rgb: Optional[dict] = None, store_out: bool = True) -> Optional[View]:
+         region_jobs: Optional["RegionJobs"] = None, rgb: Optional[dict] = None, store_out: bool = True,
+         upz: Optional["UpzRows"] = None) -> Optional[View]:
     """Launch one fused convolution (see struct E4SConv).  Returns the output view.
     `rgb` = {"rgb": [B,3,H,W], "w": [3,cout], "smod": [B,cout], "bias": [3]|None, "skip": [B,3,H/2,W/2]|None, "fir": [4,4]|None}
     adds the fused ToRGB tail (halo kernel only, see rgb_fusable); with store_out=False the activations are never written."""
@@ -261,13 +280,29 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     eng = engine or _ENGINE
     use_tc = eng == "tc" and pw.tc is not None
     use_rj = use_tc and region_jobs is not None and labels is not None
+    use_upz = use_tc and upz is not None and labels is not None and up2 and pw.tc9 is not None and \
+        (noise is None or noise.shape[1] == 1) and ch_scale is None and res is None and pixw is None and not accumulate and \
+        act in (L.ACT_NONE, L.ACT_LRELU) and in_stats is None and rgb is None
     if use_tc:
         p.tc_fmt, p.tc_out_scale = pw.tc_fmt, pw.tc_out_scale
         if TC_UNBIAS_OVERRIDE is not None:
             p.tc_unbias = TC_UNBIAS_OVERRIDE
 
+    def launch_upz():
+        z = torch.empty(upz.max_rows * 4 * pw.cout, device=x.t.device, dtype=torch.float32)
+        L.conv_upz(p, pw.tc9, pw.fir, upz.cells, upz.rows, upz.count_dev, upz.max_rows, z)
+
     def launch():
-        if use_rj and region_jobs.count is None:
+        if use_upz and upz.count is None:
+            # lazy region context: the row count on the device runs either the (cell, region) form or the poly-phase kernel
+            p.pred_count, p.pred_limit = upz.count_dev.data_ptr(), upz.limit
+            p.pred_run_if_gt = 0
+            launch_upz()
+            p.pred_run_if_gt = 1
+            L.conv(p, pw.tc)
+        elif use_upz and upz.count <= upz.limit:
+            launch_upz()
+        elif use_rj and region_jobs.count is None:
             # lazy region context: enqueue both candidates, the job count on the device runs exactly one of them
             p.pred_count, p.pred_limit = region_jobs.count_dev.data_ptr(), region_jobs.limit
             p.pred_run_if_gt = 0
@@ -292,6 +327,7 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     PROFILE.append({"stage": PROFILE_STAGE, "engine": "tc" if use_tc else "f32", "fmt": ("f16" if pw.tc_fmt == L.TC_F16 else "bf16") if use_tc else "f32",
                     "cin": pw.cin, "hout": hout, "stride": stride, "kh": pw.kh, "region_jobs": (region_jobs.count if region_jobs.count is not None else -1) if use_rj else 0, "alg_flops": alg, "exec_flops": 2.0 * m_exec * pw.k * pw.cout,
                     "m": m_exec, "k": pw.k, "n": pw.cout, "up2": bool(up2), "ev": (ev0, ev1), "rgb": rgb is not None,
+                    "upz_rows_per_cell": (float(upz.count_dev.item()) / upz.cells_total) if use_upz else 0.0,
                     "bytes": 4.0 * (b * hin * win * pw.cin + (m_exec * pw.cout if out is not None else 0) + (3 * m_exec if rgb is not None else 0))})
     return out
 
@@ -338,13 +374,25 @@ class RegionJobs:
     limit: int = 0                # lazy: run the region-job kernel iff count <= limit, the per-row kernel otherwise
 
 
+@dataclass
+class UpzRows:
+    """(cell, region) row list of one masked up-convolution resolution (e4s_upz_build_rows)."""
+    cells: torch.Tensor
+    rows: torch.Tensor
+    count_dev: torch.Tensor
+    count: Optional[int]          # None: not read back (lazy context) -> device-side predicate
+    max_rows: int
+    limit: int
+    cells_total: int
+
+
 class RegionCtx:
     """Per-forward view of the mask [B,K,Hm,Wm]: u8 label map when every pixel has at most one
     region with weight exactly 1 (the pipelines' one-hot masks), else the generic float path.
     `job_keys` = [(hout, wout, up2)] of the masked 3x3 layers whose geometry the halo kernel takes: their
     per-tile region job lists are built here and the counts come back in the same (single) D2H read as the flag."""
 
-    def __init__(self, mask: torch.Tensor, job_keys=(), lazy: bool = False, host_flag: Optional[torch.Tensor] = None):
+    def __init__(self, mask: torch.Tensor, job_keys=(), lazy: bool = False, host_flag: Optional[torch.Tensor] = None, upz_keys=()):
         """lazy=True (Generator.forward): nothing is read back while the forward is being enqueued.  The mask is ASSUMED
         one-hot (checked by `verify()` after the last launch; the caller re-runs on the generic path if not) and every
         region-job decision is a device-side launch predicate."""
@@ -353,9 +401,18 @@ class RegionCtx:
         self.mask = mask.contiguous().float()
         self.k = mask.shape[1]
         keys = list(dict.fromkeys(job_keys)) if (self.mask.is_cuda and self.k <= 32 and tc_available()) else []
-        meta = torch.zeros(1 + len(keys), device=self.mask.device, dtype=torch.int32)
+        ukeys = list(dict.fromkeys(upz_keys)) if (self.mask.is_cuda and self.k <= 32 and tc_available()) else []
+        meta = torch.zeros(1 + len(keys) + len(ukeys), device=self.mask.device, dtype=torch.int32)
         self.labels, _ = L.mask_labels(self.mask, meta[0:1])
         lists = [L.region_tile_jobs(self.labels, h, w, up, self.k, meta[1 + i:2 + i]) for i, (h, w, up) in enumerate(keys)]
+        ulists = []
+        for i, (hin, win) in enumerate(ukeys):
+            cells_total = self.mask.shape[0] * (hin + 1) * (win + 1)
+            limit = int(UPZ_RATIO * cells_total)
+            max_rows = pad_to(limit, 128)
+            slot = meta[1 + len(keys) + i:2 + len(keys) + i]
+            cells, rows = L.upz_build_rows(self.labels, hin, win, max_rows, slot)
+            ulists.append((cells, rows, slot, max_rows, limit, cells_total))
         self.lazy = bool(lazy) and self.mask.is_cuda
         if self.lazy:
             # host_flag: a pre-allocated pinned int32 buffer (CUDA-graph capture: nothing may be allocated on the host or waited
@@ -379,6 +436,9 @@ class RegionCtx:
             gh, gw = (h // 2, w // 2) if up else (h, w)
             self.region_jobs[key] = RegionJobs(jl, meta[1 + i:2 + i], None if host is None else int(host[1 + i]),
                                                b * (gh // 16) * (gw // 8))
+        self.upz = {}
+        for i, (key, (cells, rows, slot, max_rows, limit, cells_total)) in enumerate(zip(ukeys, ulists)):
+            self.upz[key] = UpzRows(cells, rows, slot, None if host is None else int(host[1 + len(keys) + i]), max_rows, limit, cells_total)
 
     def verify(self) -> bool:
         """lazy contexts: was the one-hot assumption right?  (waits only for the tiny copy issued before the first layer)"""
@@ -400,6 +460,10 @@ class RegionCtx:
         if rj.count <= 0 or rj.count > ratio * rj.tiles:
             return None
         return rj
+
+    def upz_for(self, hin: int, win: int) -> Optional["UpzRows"]:
+        """The (cell, region) row list of an up-convolution with hin x win input, if one was requested for this forward."""
+        return self.upz.get((hin, win)) if self.onehot else None
 
     @property
     def lab_hw(self):

@@ -198,13 +198,16 @@ class ModulatedConv2d(nn.Module):
         if regional and ctx is None:
             raise L.E4SError("regional styles need a mask")
         if not regional or ctx.onehot:
-            rj = None
+            rj = uz = None
             if regional:
                 _, h, w = x.bhw
                 ho, wo = (2 * h, 2 * w) if self.upsample else (h, w)
-                rj = ctx.jobs_for(ho, wo, self.upsample, E.wide_eligible(self.in_channel, self.out_channel, h, w, self.upsample))
+                if self.upsample and conv.tc9 is not None:
+                    uz = ctx.upz_for(h, w)          # conv_transpose as a (cell, region) GEMM + FIR pass (csrc/conv_tc_upz.cu)
+                if uz is None:
+                    rj = ctx.jobs_for(ho, wo, self.upsample, E.wide_eligible(self.in_channel, self.out_channel, h, w, self.upsample))
             return E.conv(x, conv, up2=self.upsample, smod=s, demod=d, regions=st.regions,
-                          labels=ctx.labels if regional else None, region_jobs=rj, **epilogue)
+                          labels=ctx.labels if regional else None, region_jobs=rj, upz=uz, **epilogue)
         # generic float masks: sum_k mask_k * conv(x; style_k), then the epilogue (model.py:395-398)
         out = None
         for r in range(st.regions):
@@ -281,7 +284,11 @@ class StyledConv(nn.Module):
 
     def forward(self, input, style, mask, noise=None):
         x = View(L.nchw_to_nhwc(input.contiguous().float()))
-        ctx = E.RegionCtx(mask) if self.mask_op else None
+        ctx = None
+        if self.mask_op:
+            mc = self.conv
+            uk = [(x.bhw[1], x.bhw[2])] if (mc.upsample and E.upz_eligible(mc.in_channel, mc.out_channel)) else []
+            ctx = E.RegionCtx(mask, upz_keys=uk)
         return L.nhwc_to_nchw(self.run(x, StyleRows.from_tensor(style), ctx, noise).t)
 
 
@@ -398,10 +405,21 @@ class Generator(nn.Module):
         res = 4
         for conv_up, conv2 in zip(self.convs[::2], self.convs[1::2]):
             res *= 2
-            if conv_up.mask_op and E.halo_geometry_ok(conv_up.conv.in_channel, conv_up.conv.out_channel, res // 2, res // 2, True):
+            if conv_up.mask_op and not E.upz_eligible(conv_up.conv.in_channel, conv_up.conv.out_channel) and \
+                    E.halo_geometry_ok(conv_up.conv.in_channel, conv_up.conv.out_channel, res // 2, res // 2, True):
                 keys.append((res, res, True))
             if conv2.mask_op and E.halo_geometry_ok(conv2.conv.in_channel, conv2.conv.out_channel, res, res, False):
                 keys.append((res, res, False))
+        return keys
+
+    def _upz_keys(self):
+        """(hin, win) of the masked up-convolutions that run as the (cell, region) conv_transpose GEMM."""
+        keys = []
+        res = 4
+        for conv_up in self.convs[::2]:
+            if conv_up.mask_op and E.upz_eligible(conv_up.conv.in_channel, conv_up.conv.out_channel):
+                keys.append((res, res))
+            res *= 2
         return keys
 
     def make_noise(self):
@@ -447,7 +465,8 @@ class Generator(nn.Module):
             raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
         # lazy region context: no device->host read while the layers are being enqueued (the one-hot assumption is checked
         # after the last launch; a soft / overlapping mask re-runs the forward on the generic per-region path)
-        ctx = _ctx if _ctx is not None else E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=True, host_flag=_host_flag)
+        ctx = _ctx if _ctx is not None else E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=True, host_flag=_host_flag,
+                                                              upz_keys=self._upz_keys())
         if ctx.k != k or ctx.mask.shape[0] != b:
             raise L.E4SError("mask and latent disagree on batch / number of regions")
 
@@ -507,7 +526,7 @@ class Generator(nn.Module):
         if not ctx.verify():
             # the mask was not one-hot: everything above used the label fast path -> redo with a synchronous context
             # (which knows) on the generic float-mask path; `noise` / styles are already resolved, so the rerun sees the same inputs
-            sync_ctx = E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=False)
+            sync_ctx = E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=False, upz_keys=self._upz_keys())
             return self.forward([latent], structure_feats, mask, return_latents=return_latents, input_is_latent=True, noise=noise,
                                 randomize_noise=randomize_noise, use_structure_code=use_structure_code, _ctx=sync_ctx)
         if return_latents:

@@ -140,6 +140,23 @@ int e4s_conv_tc_regions(const E4SConv* p, const void* w_packed, const int32_t* j
  * *count must be zeroed by the caller and receives the number of jobs (entries beyond max_jobs are dropped) */
 int e4s_region_tile_jobs(const uint8_t* labels, int batch, int lab_h, int lab_w, int hout, int wout, int up2, int32_t* jobs,
                          int32_t* count, int max_jobs, void* stream);
+/* ---- Regional up-convolution at its algorithmic cost (csrc/conv_tc_upz.cu; reference models/stylegan2/model.py:287-300,395-398) ------
+ * conv_transpose2d(stride 2) runs as a GEMM over (cell, region) rows -- cell (cy,cx), 0 <= cy <= hin, 0 <= cx <= win, holds the four
+ * values z[2cy+py, 2cx+px] of the (2hin+1) x (2win+1) transposed-convolution output and reads the 2x2 input window x[cy-1..cy, cx-1..cx];
+ * one row per region whose output pixels' 4x4 blur windows touch the cell -- and the 4x4 FIR + noise + bias + activation as a finishing
+ * pass: 9 instead of 36 cin*cout MACs per input pixel on masks with few regions per cell.
+ * e4s_upz_build_rows: labels u8 [batch, lab_h, lab_w] -> cells int32 [batch, hin+1, win+1, 2] = (region bit mask, first row) and rows
+ *   int32 [max_rows, 2] = (b << 8 | region, cy << 16 | cx); *count (zeroed by the caller) receives the number of rows, entries beyond
+ *   max_rows are dropped (both kernels of e4s_conv_tc_upz then do nothing: the caller runs e4s_conv_tc instead, E4SConv.pred_*).
+ * e4s_pack_convt_weights_f32: w [cout][cin][3][3] -> out [9][cin][cout_pad] (the 9 taps as [cin x cout] matrices in the order the kernel
+ *   consumes them), to be packed with e4s_pack_weights_tc(out, phases = 9, k = cin, cin, cout, cout_pad).
+ * e4s_conv_tc_upz: p as for e4s_conv_tc with mode E4S_CONV_UP2_POLYPHASE, labels, smod (cin % 64 == 0, cout % 128 == 0, bf16 split,
+ *   single-channel noise, NONE / LRELU); fir = the 4x4 blur kernel (Blur(pad=(1,1)), already x4); z: scratch of max_rows*4*cout floats. */
+int e4s_upz_build_rows(const uint8_t* labels, int batch, int lab_h, int lab_w, int hin, int win, int32_t* cells, int32_t* rows,
+                       int32_t* count, int max_rows, void* stream);
+int e4s_pack_convt_weights_f32(const float* w, float* out, int cout, int cin, int cout_pad, float scale, void* stream);
+int e4s_conv_tc_upz(const E4SConv* p, const void* w_packed9, const float* fir, const int32_t* cells, const int32_t* rows,
+                    const int32_t* count, int max_rows, float* z, void* stream);
 /* bytes needed for the packed tensor-core weights of a [phases, K, cout] fp32 matrix */
 int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);
 /* w_f32: [phases][K = taps*cin][cout_pad] (the e4s_conv_f32 layout) -> w_packed (hi/lo bf16, UMMA K-major SW128 tiles;
@@ -148,6 +165,8 @@ int64_t e4s_pack_weights_tc_bytes(int phases, int k, int cout);
 int e4s_debug_halo_trace(void* buf, int cap_records);
 /* debug aid: profiling experiments on the halo kernel (bit0 skip epilogue math+stores, bit1 skip tcgen05.ld, bit2 skip MMAs); 0 = normal */
 int e4s_debug_halo_flags(int flags);
+/* debug aid: profiling experiments on conv_tc_upz_kernel (bit0 skip the Z stores, bit1 skip the MMAs, bit2 skip the A gather loads, bit3 skip the TMEM reads); 0 = normal */
+int e4s_debug_upz_flags(int flags);
 int e4s_pack_weights_tc(const float* w_f32, int phases, int k, int cin, int cout, int cout_pad, void* w_packed, void* stream);
 /* same with an explicit operand format (E4S_TC_*): every weight is multiplied by `scale` (a power of two chosen by the caller so that
  * max|w|*scale ~ 2^14: keeps the fp16 lo parts out of the subnormal range) before the hi/lo split; the launch passes 1/scale as

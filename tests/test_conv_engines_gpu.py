@@ -131,3 +131,121 @@ def test_weight_pack_kernels_match_the_torch_derivation():
     got = L.pack_upconv_weights(w.cuda(), fir.cuda(), 12, 0.25).cpu()
     want = cpu_emul.pack_upconv_weights(w, fir, 12, 0.25)
     assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+
+
+UPZ_CASES = [
+    # (name, B, H, W, Cin, Cout, regions, label kind): "blocky" = 8x8 cells of the 32x32 label map, "pixel" = independent per label pixel
+    ("upz_c64_n128_blocky", 2, 16, 16, 64, 128, 4, "blocky"),
+    ("upz_c128_n256_pixel", 1, 16, 8, 128, 256, 6, "pixel"),
+    ("upz_c64_n512_odd_blocky", 2, 12, 20, 64, 512, 5, "blocky"),
+    ("upz_c512_n512_tiny", 3, 4, 4, 512, 512, 12, "pixel"),
+    ("upz_c256_n128_one_region", 1, 24, 24, 256, 128, 3, "one"),
+]
+
+
+def _upz_rows(labels, B, H, W, ratio=32.0, lazy=False):
+    from e4s2024_b200 import _lib as L
+    from e4s2024_b200 import engine as E
+    cells_total = B * (H + 1) * (W + 1)
+    max_rows = E.pad_to(int(ratio * cells_total), 128)
+    cnt = torch.zeros(1, device="cuda", dtype=torch.int32)
+    cells, rows = L.upz_build_rows(labels, H, W, max_rows, cnt)
+    return E.UpzRows(cells, rows, cnt, None if lazy else int(cnt.item()), max_rows, max_rows, cells_total)
+
+
+@pytest.mark.parametrize("case", UPZ_CASES, ids=[c[0] for c in UPZ_CASES])
+def test_upz_matches_polyphase_and_torch(case):
+    """Masked up-convolution as the (cell, region) conv_transpose GEMM + FIR pass (csrc/conv_tc_upz.cu) against the exact-fp32 poly-phase
+    engine and torch fp64 (conv_transpose2d + blur per region, masked after the blur: reference model.py:287-300,395-398)."""
+    from e4s2024_b200 import _lib as L
+    from e4s2024_b200 import engine as E
+    if not E.tc_available():
+        pytest.skip("library built without the tcgen05 engine")
+    name, B, H, W, Cin, Cout, R, kind = case
+    x = _mk((B, H, W, Cin), name + ".x")
+    w = _mk((Cout, Cin, 3, 3), name + ".w", (1.0 / (Cin * 9)) ** 0.5)
+    Ho, Wo = 2 * H, 2 * W
+    smod = (1.0 + 0.3 * _mk((B, R, Cin), name + ".s")).contiguous()
+    demod = (1.0 + 0.2 * _mk((B, R, Cout), name + ".d")).contiguous()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    if kind == "blocky":
+        labels = torch.randint(0, R, (B, 4, 4), device="cuda", dtype=torch.uint8, generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
+    elif kind == "pixel":
+        labels = torch.randint(0, R, (B, 32, 32), device="cuda", dtype=torch.uint8, generator=g)
+    else:
+        labels = torch.full((B, 32, 32), R - 1, device="cuda", dtype=torch.uint8)
+    noise = _mk((1, 1, Ho, Wo), name + ".n")
+    nw = torch.tensor([0.1], device="cuda")
+    bias = _mk((Cout,), name + ".b", 0.1)
+    fir = torch.tensor([1., 3., 3., 1.])
+    fir = (torch.outer(fir, fir) / 64 * 4).cuda()
+    pw = E.pack_up_weight(w, fir)
+    assert pw.tc is not None and pw.tc9 is not None
+    kw = dict(up2=True, smod=smod, demod=demod, labels=labels, regions=R, noise=noise, noise_w=nw, ch_shift=bias,
+              act=L.ACT_LRELU, slope=0.2, gain=2 ** 0.5)
+    y32 = E.conv(E.View(x), pw, engine="f32", **kw).t
+    uz = _upz_rows(labels, B, H, W)
+    launches = L.launch_count()
+    yz = E.conv(E.View(x), pw, engine="tc", upz=uz, **kw).t
+    assert L.launch_count() - launches == 2                     # the GEMM and the FIR pass, nothing else
+    # lazy context (count stays on the device): limit not exceeded -> same kernels, same bits; limit exceeded -> the poly-phase kernel
+    uz_lazy = _upz_rows(labels, B, H, W, lazy=True)
+    yz_lazy = E.conv(E.View(x), pw, engine="tc", upz=uz_lazy, **kw).t
+    uz_small = _upz_rows(labels, B, H, W, lazy=True)
+    uz_small.limit = 0
+    ypoly = E.conv(E.View(x), pw, engine="tc", upz=uz_small, **kw).t
+    yplain = E.conv(E.View(x), pw, engine="tc", **kw).t
+    torch.cuda.synchronize()
+    scale = float(y32.abs().max())
+    d = float((yz - y32).abs().max())
+    rows_per_cell = uz.count / uz.cells_total
+    print(f"{name}: {rows_per_cell:.2f} rows per cell, max|upz - f32| = {d:.3e} (output scale {scale:.2f})")
+    assert d < 2e-4 * max(scale, 1.0)
+    assert torch.equal(yz, yz_lazy)
+    assert torch.equal(ypoly, yplain)
+    if kind == "one":
+        assert uz.count == uz.cells_total
+
+    xd, wd = x.double().permute(0, 3, 1, 2), w.double()
+    ys = torch.arange(Ho, device="cuda") * 32 // Ho
+    xs = torch.arange(Wo, device="cuda") * 32 // Wo
+    reg = labels.long()[:, ys][:, :, xs]
+    ref = torch.zeros(B, Cout, Ho, Wo, dtype=torch.float64, device="cuda")
+    for r in range(R):
+        xm = xd * smod[:, r].double()[:, :, None, None]
+        yt = F.conv_transpose2d(xm, wd.transpose(0, 1), stride=2)
+        kf = fir.double()[None, None].repeat(Cout, 1, 1, 1)
+        yr = F.conv2d(F.pad(yt, (1, 1, 1, 1)), torch.flip(kf, [2, 3]), groups=Cout)
+        yr = yr * demod[:, r].double()[:, :, None, None]
+        ref += yr * (reg == r)[:, None].double()
+    ref = ref + 0.1 * noise.double() + bias.double()[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) * 2 ** 0.5
+    dz = float((yz.permute(0, 3, 1, 2).double() - ref).abs().max())
+    print(f"{name}: vs torch fp64: upz {dz:.3e}")
+    assert dz < 2e-4 * max(scale, 1.0)
+
+
+def test_upz_row_list_is_the_set_of_regions_reading_each_cell():
+    """e4s_upz_build_rows against a torch restatement: cell (cy,cx) lists region r iff one of the output pixels (2cy-2..2cy+2, 2cx-2..2cx+2)
+    lies in r; rows of a cell are consecutive, ascending in r, and `count` is the total."""
+    B, H, W, R = 2, 8, 12, 7
+    g = torch.Generator(device="cuda").manual_seed(11)
+    labels = torch.randint(0, R, (B, 32, 48), device="cuda", dtype=torch.uint8, generator=g)
+    uz = _upz_rows(labels, B, H, W)
+    cells, rows = uz.cells.cpu(), uz.rows.cpu()
+    lab = labels.cpu().long()
+    ys = torch.arange(2 * H) * 32 // (2 * H)
+    xs = torch.arange(2 * W) * 48 // (2 * W)
+    reg = lab[:, ys][:, :, xs]
+    total = 0
+    for b in range(B):
+        for cy in range(H + 1):
+            for cx in range(W + 1):
+                win = reg[b, max(2 * cy - 2, 0):min(2 * cy + 2, 2 * H - 1) + 1, max(2 * cx - 2, 0):min(2 * cx + 2, 2 * W - 1) + 1]
+                want = sorted(set(win.reshape(-1).tolist()))
+                mask, base = int(cells[b, cy, cx, 0]), int(cells[b, cy, cx, 1])
+                assert mask == sum(1 << r for r in want)
+                for j, r in enumerate(want):
+                    assert int(rows[base + j, 0]) == (b << 8 | r) and int(rows[base + j, 1]) == (cy << 16 | cx)
+                total += len(want)
+    assert total == uz.count
