@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   const uint32_t bar_empty = bar_full + 8 * STAGES;            // STAGES barriers
   const uint32_t bar_acc = bar_empty + 8 * STAGES;             // accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* sv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + TC_BM * 16 + 256);   // [mul | add | slope] x BN: this CTA's channels
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int phase_id = blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, TC_PRODUCER_WARPS + 1);  // 8 producer warps + the B loader's expect_tx arrive
+      mbar_init(bar_full + 8 * s, TC_PRODUCER_WARPS / 2 + 1);  // the 4 producer warps of the chunk's group + the B loader's expect_tx arrive
       mbar_init(bar_empty + 8 * s, 1);                     // one tcgen05.commit
     }
     mbar_init(bar_acc, 1);
@@ -110,6 +111,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     fence_proxy_async_smem();
   }
   if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), 2 * BN);   // [main | small-term accumulator of the fp16 mode]
+  {
+    // the layer-wide epilogue vectors of this CTA's channels, fetched once while the pipeline fills (read per 16-column block from
+    // global memory they put an L2 round trip on the critical path of every block of the epilogue)
+    const float corr0 = tc_acc_unbias(p, num_kc * (TC_BK / 16) * (f16 ? 1 : 3));
+    for (int n = tid; n < BN; n += TC_THREADS) {
+      const int gn = n_tile * BN + n;
+      sv[n] = (p.ch_scale ? __ldg(p.ch_scale + gn) : 1.f) * corr0;
+      sv[BN + n] = p.ch_shift ? __ldg(p.ch_shift + gn) : 0.f;
+      sv[2 * BN + n] = tc_epi_slope(p, gn);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -117,15 +129,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================== A producers =====================================================
+    // Two producer groups (warps 0-3 / 4-7) take the even / odd K chunks: a group issues the loads of its NEXT chunk right after
+    // publishing the current one, so two chunks of global loads are in flight per SM while each thread's fence.proxy.async (which
+    // waits for the thread's own outstanding loads) only ever sees loads it is about to consume anyway.  (Keeping two chunks in
+    // flight per THREAD does not work: the fence of chunk kc then waits for the loads of chunk kc+1.)
+    constexpr int NR = 8;             // rows per thread: r0 + 16 i
+    const int grp = warp >> 2;
     const int cg = tid & 7;           // 8-channel group inside the 64-wide K chunk
-    const int r0 = tid >> 3;          // rows r0, r0+32, r0+64, r0+96
-    int rb[4], ry[4], rx[4];
-    const float* rs[4];               // modulation row (per pixel region)
-    const float* rmean[4];
-    const float* rrstd[4];
+    const int r0 = (tid & 127) >> 3;  // rows r0, r0+16, ..., r0+112
+    int rb[NR], ry[NR], rx[NR];
+    const float* rs[NR];              // modulation row (per pixel region)
+    const float* rmean[NR];
+    const float* rrstd[NR];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const TcRow rw = rows[r0 + 32 * i];
+    for (int i = 0; i < NR; ++i) {
+      const TcRow rw = rows[r0 + 16 * i];
       rb[i] = rw.b;
       if (up) {
         ry[i] = (rw.oy >> 1) - 1;     // input row of tap u = 0
@@ -144,14 +162,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     const int ntaps = p.kh * p.kw;
     const bool grouped = (p.cin % 64) == 0;
 
-    // Grouped K order: the taps of one 64-channel group run back to back, so the per-row modulation / InstanceNorm vectors
-    // of this thread's 8 channels change only every `ntaps` chunks: keep them in registers instead of re-reading them
-    // (2 extra 16-byte loads per row and chunk, with their L1 latency exposed right before the conversion).  The
-    // InstanceNorm vectors (encoder only) stay as loads: caching them too costs 64 registers and spills.
-    float4 sreg[4][2];
-    int cached_g = -1;
-    float4 v[4][2];
-    bool ok[4];
+    float4 v[NR][2];
+    uint32_t okm = 0;
     auto prefetch = [&](int kc) {
       // K order of the packed weights (tc_chunk_k): 64-channel group outer, tap inner when cin % 64 == 0, so the taps of
       // one channel group run back to back over the same (L1-resident) input window; plain k = tap*cin + ci otherwise
@@ -169,43 +181,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         tap_ok = k0 < K;
       }
       const int ky = tap / kwid, kx = tap - ky * kwid;
+      okm = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NR; ++i) {
         int iy = ry[i] + ky, ix = rx[i] + kx;
-        ok[i] = tap_ok && rb[i] >= 0 && iy >= 0 && iy < hv && ix >= 0 && ix < wv;
-        if (ok[i]) {
+        const bool ok = tap_ok && rb[i] >= 0 && iy >= 0 && iy < hv && ix >= 0 && ix < wv;
+        if (ok) {
           iy >>= p.in_shift;
           ix >>= p.in_shift;
           const float4* src = reinterpret_cast<const float4*>(p.x + (((int64_t)rb[i] * p.hin + iy) * p.win + ix) * p.x_pitch + ci);
           v[i][0] = __ldg(src);          // allocate in L1: the 9 taps re-read these lines
           v[i][1] = __ldg(src + 1);
+          okm |= 1u << i;
         }
       }
     };
 
-    prefetch(0);
-    for (int kc = 0; kc < num_kc; ++kc) {
+    if (grp < num_kc) prefetch(grp);
+    for (int kc = grp; kc < num_kc; kc += 2) {
       const int s = kc % STAGES;
       const uint32_t par = (kc / STAGES) & 1;
       mbar_wait(bar_empty + 8 * s, par ^ 1);
       uint8_t* a_hi = smem + s * STAGE_BYTES;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
       const int ci = grouped ? (kc / ntaps) * 64 + cg * 8 : (kc * TC_BK + cg * 8) % p.cin;
-      const int gcur = grouped ? kc / ntaps : kc;
-      if (gcur != cached_g) {
-        cached_g = gcur;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (rs[i]) {
-            sreg[i][0] = __ldg(reinterpret_cast<const float4*>(rs[i] + ci)); sreg[i][1] = __ldg(reinterpret_cast<const float4*>(rs[i] + ci) + 1);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = r0 + 32 * i;
+      for (int i = 0; i < NR; ++i) {
+        const int row = r0 + 16 * i;
         float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (ok[i]) {
+        if ((okm >> i) & 1u) {
           f[0] = v[i][0].x; f[1] = v[i][0].y; f[2] = v[i][0].z; f[3] = v[i][0].w;
           f[4] = v[i][1].x; f[5] = v[i][1].y; f[6] = v[i][1].z; f[7] = v[i][1].w;
           if (rmean[i]) {
@@ -214,8 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
             f[0] = (f[0] - m0.x) * q0.x; f[1] = (f[1] - m0.y) * q0.y; f[2] = (f[2] - m0.z) * q0.z; f[3] = (f[3] - m0.w) * q0.w;
             f[4] = (f[4] - m1.x) * q1.x; f[5] = (f[5] - m1.y) * q1.y; f[6] = (f[6] - m1.z) * q1.z; f[7] = (f[7] - m1.w) * q1.w;
           }
-          if (rs[i]) {
-            const float4 s0 = sreg[i][0], s1 = sreg[i][1];
+          if (rs[i]) {          // per-row style modulation (L1-resident rows of the table)
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(rs[i] + ci)), s1 = __ldg(reinterpret_cast<const float4*>(rs[i] + ci) + 1);
             f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
             f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
           }
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      if (kc + 1 < num_kc) prefetch(kc + 1);
+      if (kc + 2 < num_kc) prefetch(kc + 2);
     }
 
     // =========================== epilogue ========================================================
@@ -272,15 +276,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         float4 mul[4], add[4], sl[4];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const int n = n_base + c0 + 4 * qd;
-          mul[qd] = drow ? ldg4(drow + n) : make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.ch_scale) {
-            const float4 sc = ldg4(p.ch_scale + n);
-            mul[qd].x *= sc.x; mul[qd].y *= sc.y; mul[qd].z *= sc.z; mul[qd].w *= sc.w;
+          const int n = n_base + c0 + 4 * qd, nl = half * (BN / 2) + c0 + 4 * qd;
+          mul[qd] = *reinterpret_cast<const float4*>(sv + nl);                     // channel scale x accumulate un-bias
+          if (drow) {
+            const float4 dm = ldg4(drow + n);
+            mul[qd].x *= dm.x; mul[qd].y *= dm.y; mul[qd].z *= dm.z; mul[qd].w *= dm.w;
           }
-          mul[qd].x *= corr; mul[qd].y *= corr; mul[qd].z *= corr; mul[qd].w *= corr;
-          add[qd] = p.ch_shift ? ldg4(p.ch_shift + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-          sl[qd] = make_float4(tc_epi_slope(p, n), tc_epi_slope(p, n + 1), tc_epi_slope(p, n + 2), tc_epi_slope(p, n + 3));
+          add[qd] = *reinterpret_cast<const float4*>(sv + BN + nl);
+          sl[qd] = *reinterpret_cast<const float4*>(sv + 2 * BN + nl);
         }
         if (p.res && live) {
 #pragma unroll

@@ -17,7 +17,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // one bf16 A tile (hi or lo): 16
 __host__ __device__ constexpr int tc_block_n(int cout) { return cout >= 256 ? 256 : cout; }
 __host__ __device__ constexpr int tc_stage_bytes(int bn) { return 2 * TC_A_BYTES + 2 * bn * TC_BK * 2; }
 __host__ __device__ constexpr int tc_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 3 : (bn == 64 ? 4 : 5)); }
-__host__ __device__ constexpr int tc_smem_bytes(int bn) { return tc_stages(bn) * tc_stage_bytes(bn) + TC_BM * 16 + 256 + 1024; }
+__host__ __device__ constexpr int tc_smem_bytes(int bn) { return tc_stages(bn) * tc_stage_bytes(bn) + TC_BM * 16 + 256 + 3 * bn * 4 + 1024; }   // + [mul | add | slope] epilogue vectors
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
