@@ -57,6 +57,7 @@ EXPORTS = [
     "e4s_residual_combine_f32", "e4s_masked_mean_f32", "e4s_mask_member_bits_u32", "e4s_masked_mean_ws_bytes", "e4s_masked_mean_bits_f32", "e4s_resize_bilinear_nchw_to_nhwc_f32",
     "e4s_resize_bilinear_nhwc_to_nchw_f32", "e4s_maxpool3x3s2_nhwc_f32", "e4s_upsample_argmax_u8",
     "e4s_bicubic_down_norm_f32", "e4s_labels_to_onehot_f32", "e4s_swap_comp_styles_f32", "e4s_tensor2im_u8", "e4s_im2tensor_f32", "e4s_morphology_f32", "e4s_depthwise_conv_f32", "e4s_soft_erosion_finish_f32", "e4s_pyr_down_f32", "e4s_pyr_up_f32", "e4s_pyr_blend_f32",
+    "e4s_conv_wgrad_ws_bytes", "e4s_conv_wgrad_f32", "e4s_region_scale_f32", "e4s_region_dot_ws_bytes", "e4s_region_dot_f32", "e4s_chan_scale_accum_f32",
 ]
 
 _lib = None
@@ -78,6 +79,8 @@ def lib() -> C.CDLL:
         _lib.e4s_chan_stats_ws_bytes.restype = C.c_int64
         _lib.e4s_pack_weights_tc_bytes.restype = C.c_int64
         _lib.e4s_masked_mean_ws_bytes.restype = C.c_int64
+        _lib.e4s_conv_wgrad_ws_bytes.restype = C.c_int64
+        _lib.e4s_region_dot_ws_bytes.restype = C.c_int64
         if _lib.e4s_sizeof_conv() != C.sizeof(E4SConv):
             raise E4SError(f"struct E4SConv mismatch: C {_lib.e4s_sizeof_conv()} vs ctypes {C.sizeof(E4SConv)}")
     return _lib
@@ -537,3 +540,59 @@ def bicubic_down_norm(x, factor, taps, mean, std, c_pad, clamp=True):
                                            _stream()),
            "e4s_bicubic_down_norm_f32")
     return y
+
+
+# ---- backward pass ---------------------------------------------------------------
+
+def _ws(tag: str, device, nbytes: int) -> torch.Tensor:
+    key = (tag, device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def conv_wgrad(x: torch.Tensor, cin: int, g: torch.Tensor, cout: int, loop_hw, kh: int, kw: int, geom, sscale: Optional[torch.Tensor],
+               scale: float, dw: torch.Tensor, accumulate: bool):
+    """x [B,Hx,Wx,Px], g [B,Hg,Wg,Pg] NHWC (first cin / cout channels); geom = (tx, px, sg, tg, pg); sscale [B, >=cin] (row stride
+    sscale.stride(0)) or None; dw [cout, cin, kh, kw] contiguous (see e4s_conv_wgrad_f32)."""
+    b, hx, wx, pxp = x.shape
+    _, hg, wg, pgp = g.shape
+    hl, wl = loop_hw
+    tx, px, sg, tg, pg = geom
+    assert dw.is_contiguous() and tuple(dw.shape) == (cout, cin, kh, kw), (dw.shape, (cout, cin, kh, kw))
+    ws = _ws("wgrad", x.device, int(lib().e4s_conv_wgrad_ws_bytes(b, hl, wl, cin, cout, kh, kw)))
+    _check(lib().e4s_conv_wgrad_f32(_fp(x.data_ptr()), C.c_int64(pxp), b, hx, wx, cin, _fp(g.data_ptr()), C.c_int64(pgp), hg, wg, cout, hl, wl,
+                                    kh, kw, tx, px, sg, tg, pg, _fp(_p(sscale)), C.c_int64(0 if sscale is None else sscale.stride(0)), _f32(scale),
+                                    _fp(dw.data_ptr()), int(accumulate), _fp(ws.data_ptr()), _stream()), "e4s_conv_wgrad_f32")
+
+
+def region_scale(g: torch.Tensor, c: int, table: Optional[torch.Tensor], labels: Optional[torch.Tensor], regions: int, select: int = -1,
+                 out_c: Optional[int] = None) -> torch.Tensor:
+    """g [B,H,W,P] -> [B,H,W,out_c]: g * table[b, r(p)] on the pixels of region `select` (-1: all), zero elsewhere / in the channel padding."""
+    b, h, w, pitch = g.shape
+    out_c = (c + 3) // 4 * 4 if out_c is None else out_c
+    out = torch.empty(b, h, w, out_c, device=g.device, dtype=torch.float32)
+    lh, lw = (labels.shape[1], labels.shape[2]) if labels is not None else (0, 0)
+    _check(lib().e4s_region_scale_f32(_fp(g.data_ptr()), C.c_int64(pitch), b, h, w, c, _fp(_p(table)), _fp(_p(labels)), regions, lh, lw, int(select),
+                                      _fp(out.data_ptr()), C.c_int64(out_c), out_c, _stream()), "e4s_region_scale_f32")
+    return out
+
+
+def region_dot(a: torch.Tensor, b_: torch.Tensor, c: int, labels: Optional[torch.Tensor], regions: int) -> torch.Tensor:
+    """a, b_ [B,H,W,P*] -> [B, regions, c]: per-region sums of a*b (labels None: regions must be 1)."""
+    b, h, w, pa = a.shape
+    out = torch.empty(b, regions, c, device=a.device, dtype=torch.float32)
+    lh, lw = (labels.shape[1], labels.shape[2]) if labels is not None else (0, 0)
+    ws = _ws("rdot", a.device, int(lib().e4s_region_dot_ws_bytes(b, h, w, c, regions)))
+    _check(lib().e4s_region_dot_f32(_fp(a.data_ptr()), C.c_int64(pa), _fp(b_.data_ptr()), C.c_int64(b_.shape[3]), b, h, w, c, _fp(_p(labels)), regions,
+                                    lh, lw, _fp(out.data_ptr()), _fp(ws.data_ptr()), _stream()), "e4s_region_dot_f32")
+    return out
+
+
+def chan_scale_accum(h: torch.Tensor, c: int, s: Optional[torch.Tensor], dx: torch.Tensor, accumulate: bool):
+    """dx[b,y,x,:c] (+)= h[b,y,x,:c] * s[b,:c]; s [B, >=c] with row stride s.stride(0), or None."""
+    b, hh, ww, ph = h.shape
+    _check(lib().e4s_chan_scale_accum_f32(_fp(h.data_ptr()), C.c_int64(ph), _fp(_p(s)), C.c_int64(0 if s is None else s.stride(0)), _fp(dx.data_ptr()),
+                                          C.c_int64(dx.shape[3]), b, C.c_int64(hh * ww), c, int(accumulate), _stream()), "e4s_chan_scale_accum_f32")

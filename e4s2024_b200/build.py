@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libe4s_b200.so")
-SOURCES = ["core.cu", "pack.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_halo.cu", "conv_tc_wide.cu", "conv_tc_upz.cu", "pointwise.cu", "norm_pool.cu", "resize.cu", "paste.cu"]
+SOURCES = ["core.cu", "pack.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_halo.cu", "conv_tc_wide.cu", "conv_tc_upz.cu", "pointwise.cu", "norm_pool.cu", "resize.cu", "paste.cu", "backward.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-DE4S_BUILD"] + (["-DE4S_HL_ACCT"] if os.environ.get("E4S_HL_ACCT") else [])

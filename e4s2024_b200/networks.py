@@ -66,7 +66,7 @@ class Net3(nn.Module):
                                       num_w_layers=self.remaining_layer_idx if self.remaining_layer_idx != 17 else 18))
         self.G = Generator(size=self.opts.out_size, style_dim=512, n_mlp=8, split_layer_idx=self.split_layer_idx,
                            remaining_layer_idx=self.remaining_layer_idx)
-        for p in self.parameters():          # inference drop-in: nothing here trains
+        for p in self.encoder.parameters():  # the encoder has no backward here (PTI tunes the MLPs and the generator from stored style vectors)
             p.requires_grad = False
         self._bias_cache = None
         E.install_pack_invalidation(self)
@@ -147,8 +147,36 @@ class Net3(nn.Module):
     def _get_style_vectors_impl(self, img, mask):
         return self._encode(img, mask)
 
+    def _codes_train(self, style_vectors):
+        """_codes through the differentiable EqualLinear (stylegan2/grad.py): what the PTI coach back-propagates into the LocalMLPs."""
+        from .stylegan2 import grad as GR
+        sv = style_vectors.float()
+        b, k, d = sv.shape
+        rl = self.remaining_layer_idx
+        add_avg = bool(self.opts.start_from_latent_avg)
+        if add_avg and getattr(self.opts, "learn_in_w", False):
+            raise NotImplementedError("learn_in_w=True is not used by the released pipelines")
+        outs = []
+        for i in range(k):
+            m = self.MLPs[i]
+            h = GR.equal_linear(m.mlp[0], sv[:, i].contiguous())
+            h = torch.nn.functional.leaky_relu(h, m.mlp[1].negative_slope)
+            outs.append(GR.equal_linear(m.mlp[2], h).view(b, m.num_w_layers, m.dim_style))
+        codes = torch.stack(outs, dim=1)                                  # [B, K, L, 512]
+        if add_avg:
+            la = self.latent_avg.to(sv.device).float()
+            codes = codes + la[:codes.shape[2]]
+            if rl != 17:
+                codes = torch.cat([codes, la[rl:].expand(b, k, 18 - rl, 512)], dim=2)
+        return codes
+
+    def _train_path(self, anchor):
+        return anchor is not None and self.training and anchor.is_cuda
+
     def cal_style_codes(self, style_vectors):
         anchor = grad_anchor(self, (style_vectors,))
+        if self._train_path(anchor):
+            return self._codes_train(style_vectors)
         with torch.no_grad():
             out = self._cal_style_codes_impl(style_vectors)
         return inference_only(out, anchor)
@@ -158,6 +186,8 @@ class Net3(nn.Module):
 
     def gen_img(self, struc_codes, style_codes, mask, randomize_noise=True, noise=None, return_latents=False):
         anchor = grad_anchor(self, (style_codes,))
+        if self._train_path(anchor):
+            return self._gen_img_impl(struc_codes, style_codes, mask, randomize_noise, noise, return_latents)      # G.forward takes its train() path
         with torch.no_grad():
             out = self._gen_img_impl(struc_codes, style_codes, mask, randomize_noise, noise, return_latents)
         return inference_only(out, anchor)

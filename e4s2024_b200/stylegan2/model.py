@@ -441,10 +441,28 @@ class Generator(nn.Module):
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
                 use_structure_code=False, _ctx=None, _host_flag=None):
         anchor = grad_anchor(self, (styles,))
+        if anchor is not None and self.training and anchor.is_cuda and _ctx is None:
+            # train() mode + autograd recording (the PTI coach: training/video_swap_ft_coach.py:242-318): the differentiable path
+            return self._forward_train(styles, structure_feats, mask, return_latents, truncation, input_is_latent, noise, randomize_noise,
+                                       use_structure_code)
         with torch.no_grad():
             out = self._forward(styles, structure_feats, mask, return_latents, inject_index, truncation, truncation_latent,
                                 input_is_latent, noise, randomize_noise, use_structure_code, _ctx, _host_flag)
         return inference_only(out, anchor)
+
+    def _forward_train(self, styles, structure_feats, mask, return_latents, truncation, input_is_latent, noise, randomize_noise,
+                       use_structure_code):
+        from . import grad as GR
+        if not input_is_latent or truncation < 1 or len(styles) != 1 or styles[0].ndim != 4:
+            raise L.E4SError("the differentiable path takes styles=[latent [B,K,n_latent,512]] with input_is_latent=True (what Net3.gen_img passes)")
+        latent = styles[0].float()
+        if latent.shape[3] != self.style_dim or latent.shape[2] < self.n_latent:
+            raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
+        if noise is None:
+            noise = [None] * self.num_layers if randomize_noise else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        E.invalidate_packs(self)          # optimisers update weights in place through .data (no version bump): never trust a cached packing here
+        image, feats = GR.generator_forward(self, latent, mask, noise, structure_feats, use_structure_code)
+        return (image, latent, feats) if return_latents else (image, None, feats)
 
     def _forward(self, styles, structure_feats, mask, return_latents, inject_index, truncation, truncation_latent, input_is_latent,
                  noise, randomize_noise, use_structure_code, _ctx, _host_flag):
@@ -534,8 +552,8 @@ class Generator(nn.Module):
         return image, None, intermediate_feats
 
 
-_NO_BACKWARD = ("the B200 drop-in is inference-only: there is no backward through the fused modulated convolution. Run PTI / training "
-                "on the reference modules and load the tuned weights here with load_state_dict().")
+_NO_BACKWARD = ("this forward ran on the inference-only path: gradients flow through Generator / Net3.gen_img / Net3.cal_style_codes only in "
+                "train() mode on CUDA tensors (as the PTI coach uses them); the encoder and the face parser have no backward.")
 
 
 class _InferenceOnly(torch.autograd.Function):

@@ -313,6 +313,33 @@ int e4s_pyr_up_f32(const float* x, const float* other, float* out, int64_t plane
 int e4s_pyr_blend_f32(const float* la, const float* lb, const float* gm, float* out, int batch, int channels, int m_channels, int h, int w,
                       void* stream);
 
+/* ---- backward pass of the regional modulated convolution (PTI fine-tuning, reference training/video_swap_ft_coach.py:242-318
+ * calls loss.backward() through net.G; the reference differentiates its convolutions through models/stylegan2/op/conv2d_gradfix.py:134-225).
+ * Data gradients re-use e4s_conv_tc / e4s_conv_f32 with transposed weights; these entry points cover the rest.  NHWC fp32 throughout.
+ *
+ * e4s_conv_wgrad_f32: dw[co][ci][ky][kx] (+)= scale * sum_b sum_{y < hl, x < wl} sscale[b*s_stride + ci] *
+ *        x[b, y + ky*tx - px, x + kx*tx - px, ci] * g[b, y*sg + ky*tg - pg, x*sg + kx*tg - pg, co]      (out-of-range taps contribute 0)
+ *   same-resolution k x k conv (pad k/2): hl x wl = output size, tx = 1, px = k/2, sg = 1, tg = 0, pg = 0
+ *   conv_transpose2d(stride 2):          hl x wl = input size,  tx = 0, px = 0,   sg = 2, tg = 1, pg = 0 (g on the (2h+1) x (2w+1) grid)
+ *   F.linear:                            kh = kw = 1, hl = rows, wl = 1
+ *   sscale may be NULL.  Deterministic (fixed split over pixel chunks, ordered second pass); ws: e4s_conv_wgrad_ws_bytes bytes.
+ * e4s_region_scale_f32: out[p, c] = g[p, c] * table[(b*regions + r(p))*c + c] for c < c (table may be NULL), 0 for c <= ch < out_c (channel
+ *   padding) and for every pixel whose region differs from select_region (>= 0; -1 keeps all): the reference's `* mask_k` (model.py:395-398).
+ * e4s_region_dot_f32: out[b, r, c] = sum over the pixels p of sample b with r(p) == r of a[p,c] * b[p,c] (labels NULL: one region).
+ *   fp64 partial sums over fixed 1024-pixel chunks, ordered reduction; ws: e4s_region_dot_ws_bytes bytes.
+ * e4s_chan_scale_accum_f32: dx[p, c] (+)= h[p, c] * s[b*s_stride + c]  (s may be NULL: plain copy / accumulate). */
+int64_t e4s_conv_wgrad_ws_bytes(int batch, int hl, int wl, int cin, int cout, int kh, int kw);
+int e4s_conv_wgrad_f32(const float* x, int64_t x_pitch, int batch, int hx, int wx, int cin, const float* g, int64_t g_pitch, int hg, int wg,
+                       int cout, int hl, int wl, int kh, int kw, int tx, int px, int sg, int tg, int pg, const float* sscale,
+                       int64_t s_stride, float scale, float* dw, int accumulate, void* ws, void* stream);
+int e4s_region_scale_f32(const float* g, int64_t g_pitch, int batch, int h, int w, int c, const float* table, const uint8_t* labels,
+                         int regions, int lab_h, int lab_w, int select_region, float* out, int64_t out_pitch, int out_c, void* stream);
+int64_t e4s_region_dot_ws_bytes(int batch, int h, int w, int c, int regions);
+int e4s_region_dot_f32(const float* a, int64_t a_pitch, const float* b, int64_t b_pitch, int batch, int h, int w, int c,
+                       const uint8_t* labels, int regions, int lab_h, int lab_w, float* out, void* ws, void* stream);
+int e4s_chan_scale_accum_f32(const float* h, int64_t h_pitch, const float* s, int64_t s_stride, float* dx, int64_t dx_pitch, int batch,
+                             int64_t hw, int c, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,7 @@ def load(mod, shapes_seed, dev):
     new = synth.fill_state_dict({k: v.shape for k, v in sd.items()}, seed=shapes_seed)
     sd.update({k: v.to(sd[k].dtype) for k, v in new.items()})
     mod.load_state_dict(sd)
-    return mod.to("cpu" if dev == "emul" else "cuda")
+    return mod.to("cpu" if dev == "emul" else "cuda").eval()        # the pipelines run the modules in eval() mode
 
 
 def maxdiff(a, b):
@@ -127,8 +127,8 @@ def test_generator_small(golden, dev, tag):
     assert lat is None and img.shape == (2, 3, size, size)
     assert maxdiff(img, g["image"]) < 1e-3
     assert maxdiff(inter[:, ::16], g["inter"]) < 1e-3
-    # parameters that require grad + autograd recording (what the reference pipeline's PTI step does): the forward still works
-    # like the reference's, and backward fails with a message that says why (not autograd's "does not require grad")
+    # eval() mode with parameters that require grad + autograd recording: the forward is the inference path, and backward fails with a
+    # message that says why (not autograd's "does not require grad"); gradients exist in train() mode (tests/test_backward_gpu.py)
     from e4s2024_b200._lib import E4SError
     assert img.requires_grad
     with pytest.raises(E4SError, match="inference-only"):
