@@ -109,7 +109,7 @@ def build_path(dev, seed_net=9, seed_seg=10):
     from e4s2024_b200.sharding import SwapHotPath
     net = Net3(net3_opts())
     sd_net = synth.synth_module_weights(net, seed=seed_net)
-    net = net.to(dev)
+    net = net.to(dev).eval()
     la = synth.randn("net3.latent_avg", (18, 512), seed_net, 0.1)
     net.latent_avg = la.to(dev)
     parser = FaceParser(seg_ckpt=None, size=SIZE, device=str(dev))

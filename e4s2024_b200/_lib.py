@@ -169,10 +169,11 @@ def pack_convt_weights(w: torch.Tensor, cout_pad: int, scale: float = 1.0) -> to
     return out
 
 
-def conv_upz(params: E4SConv, tc9: torch.Tensor, fir: torch.Tensor, cells: torch.Tensor, rows: torch.Tensor, count: torch.Tensor,
-             max_rows: int, z: torch.Tensor):
-    _check(lib().e4s_conv_tc_upz(C.byref(params), _fp(tc9.data_ptr()), _fp(fir.data_ptr()), _fp(cells.data_ptr()), _fp(rows.data_ptr()),
-                                 _fp(count.data_ptr()), int(max_rows), _fp(z.data_ptr()), _stream()), "e4s_conv_tc_upz")
+def conv_upz(params: E4SConv, tc9: torch.Tensor, fir: torch.Tensor, cells: Optional[torch.Tensor], rows: Optional[torch.Tensor],
+             count: Optional[torch.Tensor], max_rows: int, z: torch.Tensor):
+    """cells / rows / count None: the direct (un-masked) form, max_rows = batch * (hin+1) * (win+1)."""
+    _check(lib().e4s_conv_tc_upz(C.byref(params), _fp(tc9.data_ptr()), _fp(fir.data_ptr()), _fp(_p(cells)), _fp(_p(rows)),
+                                 _fp(_p(count)), int(max_rows), _fp(z.data_ptr()), _stream()), "e4s_conv_tc_upz")
 
 
 def conv_batched(params_list):
@@ -420,7 +421,7 @@ def _stats_ws(device, batch, c) -> torch.Tensor:
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < n:
-        ws = torch.empty(max(n, 1 << 20), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(n, 1 << 20), dtype=torch.uint8, device=device)      # zero-filled: the kernel's arrival counters (e4s_b200.h)
         _ws_cache[key] = ws
     return ws
 

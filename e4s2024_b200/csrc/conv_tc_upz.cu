@@ -37,10 +37,15 @@ constexpr int UZ_SMEM = 2 * UZ_A_STAGE + UZ_B_STAGES * UZ_B_STAGE + TC_BM * 16 +
 // sub-steps consume them: W[1][0] W[0][0] | W[0][1] W[1][1] | W[1][2] W[0][2] | W[2][0] W[2][1] | W[2][2].
 __device__ __constant__ int c_uz_order[9] = {3, 0, 1, 4, 5, 2, 6, 7, 8};
 
+// SW = output channels per CTA = width of one phase slot in TMEM (128; 64 / 32 for the un-masked 512^2 / 1024^2 layers whose cout is that
+// small).  rowlist == nullptr: DIRECT mode for un-masked layers -- row i is cell i of the [batch, hin+1, win+1] cell grid, region 0, and
+// max_rows is the exact row count (no list, no counter).
+template <int SW>
 __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int bn_packed,
                                                                     const int2* __restrict__ rowlist, const int* __restrict__ count,
                                                                     const int max_rows, float* __restrict__ z, const int dbg) {
-  const int nrows = __ldg(count);
+  constexpr int SLOT_B = SW * 128;                    // SW weight rows of one 64-wide K chunk (hi or lo)
+  const int nrows = rowlist ? __ldg(count) : max_rows;
   if (nrows > max_rows) return;                                                                    // the list overflowed: the caller's fallback runs
   if (p.pred_count != nullptr && ((__ldg(p.pred_count) > p.pred_limit) != (p.pred_run_if_gt != 0))) return;
   const int row0 = (int)blockIdx.x * TC_BM;
@@ -65,8 +70,14 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
   if (tid < TC_BM) {
     int4 rw = make_int4(-1, 0, 0, 0);
     if (row0 + tid < nrows) {
-      const int2 e = __ldg(rowlist + row0 + tid);
-      rw = make_int4(e.x >> 8, e.y >> 16, e.y & 0xffff, e.x & 0xff);      // b, cy, cx, region
+      if (rowlist) {
+        const int2 e = __ldg(rowlist + row0 + tid);
+        rw = make_int4(e.x >> 8, e.y >> 16, e.y & 0xffff, e.x & 0xff);    // b, cy, cx, region
+      } else {
+        const int cwd = p.win + 1, cpp = (p.hin + 1) * cwd, i = row0 + tid;
+        const int b = i / cpp, rem = i - b * cpp;
+        rw = make_int4(b, rem / cwd, rem % cwd, 0);
+      }
     }
     rows[tid] = rw;
   }
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), 4 * SW);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,34 +199,37 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
     tc_fence_after();
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int hh = warp >> 2;               // slot pair (2hh, 2hh + 1)
-    const int n_base = (int)blockIdx.y * 128;
-    float* stage = reinterpret_cast<float*>(smem + warp * (32 * 512));                  // 32 rows x 128 floats, float4 index ^= row % 8
+    const int n_base = (int)blockIdx.y * SW;
+    constexpr int F4 = SW / 4;                                                          // float4 per staged row
+    constexpr int RPI = 32 / F4;                                                        // rows written per warp instruction (1, 2 or 4)
+    float* stage = reinterpret_cast<float*>(smem + warp * (32 * SW * 4));               // 32 rows x SW floats, float4 index ^= row % 8
 #pragma unroll 1
     for (int sl = 2 * hh; sl < 2 * hh + 2; ++sl) {
       const int zslot = sl == 0 ? 2 : (sl == 1 ? 0 : (sl == 2 ? 1 : 3));                  // (py,px) -> py*2 + px
       const int taps = sl == 1 ? 4 : (sl == 3 ? 1 : 2);
       const float corr = tc_acc_unbias(p, ngroups * 4 * taps * 3);                        // accumulate steps into this slot
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < SW; c0 += 32) {
         if (dbg & 8) break;
         uint32_t acc[32];
-        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * 128 + c0), acc);   // warp-collective
+        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * SW + c0), acc);   // warp-collective
         tmem_wait_ld32(acc);
 #pragma unroll
         for (int qd = 0; qd < 8; ++qd) {
           const int f = (c0 >> 2) + qd;
-          *reinterpret_cast<uint4*>(stage + lane * 128 + ((f ^ (lane & 7)) << 2)) = make_uint4(acc[4 * qd], acc[4 * qd + 1], acc[4 * qd + 2], acc[4 * qd + 3]);
+          *reinterpret_cast<uint4*>(stage + lane * SW + ((f ^ (lane & 7)) << 2)) = make_uint4(acc[4 * qd], acc[4 * qd + 1], acc[4 * qd + 2], acc[4 * qd + 3]);
         }
       }
       __syncwarp();
 #pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int4 rw = rows[q * 32 + r];                                                 // warp-uniform
-        if (rw.x < 0) break;                                                              // rows beyond the list are at the end of the tile
-        float4 a = *reinterpret_cast<const float4*>(stage + r * 128 + ((lane ^ (r & 7)) << 2));
+      for (int r0_ = 0; r0_ < 32; r0_ += RPI) {
+        const int r = r0_ + lane / F4, f = lane % F4;                                    // RPI rows per instruction, F4 lanes each
+        const int4 rw = rows[q * 32 + r];
+        if (rw.x < 0) continue;                                                           // rows beyond the list are at the end of the tile
+        float4 a = *reinterpret_cast<const float4*>(stage + r * SW + ((f ^ (r & 7)) << 2));
         a.x *= corr; a.y *= corr; a.z *= corr; a.w *= corr;      // demodulation is applied after the FIR (finishing pass): one region per output pixel
         if ((dbg & 1) && a.x != 123456.789f) continue;
-        *reinterpret_cast<float4*>(z + (((int64_t)row0 + q * 32 + r) * 4 + zslot) * p.cout + n_base + 4 * lane) = a;
+        *reinterpret_cast<float4*>(z + (((int64_t)row0 + q * 32 + r) * 4 + zslot) * p.cout + n_base + 4 * f) = a;
       }
       __syncwarp();
     }
@@ -223,8 +237,8 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
   } else if (warp == TC_PRODUCER_WARPS) {
     // =========================== MMA issuer ========================================================
     constexpr uint32_t D_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);    // SBO 1024, version 1, SWIZZLE_128B
-    const uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * SW) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = two slots
+    const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);         // N = one slot
     int bcount = 0;
     for (int step = 0; step < nsteps; ++step) {
       const int s = step & 1;
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
       const int nsub = tap == 0 ? 2 : 1;
       for (int sub = 0; sub < nsub; ++sub) {
         const uint32_t idesc = tap == 3 ? idesc128 : idesc256;
-        const uint32_t col = tap == 0 ? (uint32_t)(sub * 256) : (tap == 1 ? 0u : 128u);
+        const uint32_t col = tap == 0 ? (uint32_t)(sub * 2 * SW) : (tap == 1 ? 0u : (uint32_t)SW);
         const uint32_t tacc = tmem_acc + col;
         // The weights of a sub-step arrive as two ring stages, hi then lo (32 KB each: the ring holds four stages in flight, which
         // hides the ~1 us L2 -> shared-memory latency of a bulk copy behind the MMAs of the stages before it; with two 64 KB stages
@@ -296,13 +310,13 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
     // packed chunk (e4s_pack_weights_tc, 9 phases, K = cin): per (n_tile, group): [hi tiles of the 9 blocks | lo tiles], bn_packed rows each
     const int64_t t_bytes = (int64_t)bn_packed * 128;
     const int cb = (int)blockIdx.y;
-    const int nt = cb * 128 / bn_packed;
+    const int nt = cb * SW / bn_packed;
     int bcount = 0;
     for (int step = 0; step < nsteps; ++step) {
       const int g = step >> 2, tap = step & 3;
       const int nsub = tap == 0 ? 2 : 1;
       for (int sub = 0; sub < nsub; ++sub) {
-        const uint8_t* base = wpk + ((int64_t)nt * ngroups + g) * (18 * t_bytes) + (int64_t)(cb * 128 % bn_packed) * 128;
+        const uint8_t* base = wpk + ((int64_t)nt * ngroups + g) * (18 * t_bytes) + (int64_t)(cb * SW % bn_packed) * 128;
         const int qs = tap == 0 ? sub : tap + 1;           // sub-step 0..4 of the group
         for (int half = 0; half < 2; ++half, ++bcount) {   // hi blocks, then lo blocks (9 block tiles further on)
           const int bs = bcount & (UZ_B_STAGES - 1);
@@ -310,12 +324,12 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
           const uint32_t dst = smem_base + B_OFF + bs * UZ_B_STAGE;
           if (elect_one()) {
             if (qs < 4) {                                    // blocks 2qs, 2qs+1
-              mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * UZ_SLOT);
-              bulk_g2s(dst, base + (9 * half + 2 * qs) * t_bytes, UZ_SLOT, bar_bfull + 8 * bs);
-              bulk_g2s(dst + UZ_SLOT, base + (9 * half + 2 * qs + 1) * t_bytes, UZ_SLOT, bar_bfull + 8 * bs);
+              mbar_arrive_expect_tx(bar_bfull + 8 * bs, 2 * SLOT_B);
+              bulk_g2s(dst, base + (9 * half + 2 * qs) * t_bytes, SLOT_B, bar_bfull + 8 * bs);
+              bulk_g2s(dst + SLOT_B, base + (9 * half + 2 * qs + 1) * t_bytes, SLOT_B, bar_bfull + 8 * bs);
             } else {                                         // block 8
-              mbar_arrive_expect_tx(bar_bfull + 8 * bs, UZ_SLOT);
-              bulk_g2s(dst, base + (9 * half + 8) * t_bytes, UZ_SLOT, bar_bfull + 8 * bs);
+              mbar_arrive_expect_tx(bar_bfull + 8 * bs, SLOT_B);
+              bulk_g2s(dst, base + (9 * half + 8) * t_bytes, SLOT_B, bar_bfull + 8 * bs);
             }
           }
           __syncwarp();
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(UZ_THREADS, 1) conv_tc_upz_kernel(const E4SCon
   __syncthreads();
   if (warp == TC_PRODUCER_WARPS) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, 512);
+    tmem_dealloc(tmem_acc, 4 * SW);
   }
 }
 
@@ -554,6 +568,87 @@ __global__ void __launch_bounds__(256, 2) upz_blur_kernel(const E4SConv p, const
   }
 }
 
+// Finishing pass of the DIRECT (un-masked) mode: row = cell index, one style per sample -- no labels, no lookups.  A thread owns one input
+// pixel (a, bx) = 2x2 output pixels and four channels; LPP = min(cout, 128) / 4 threads share a pixel, consecutive thread groups take
+// consecutive pixels of a row, so the 25 window loads and the 4 stores of a warp are contiguous runs.
+__global__ void __launch_bounds__(256) upz_blur_direct_kernel(const E4SConv p, const float* __restrict__ z, const float* __restrict__ fir,
+                                                              const int lpp, const int64_t npix) {
+  const int ppb = 256 / lpp;
+  const int64_t pixi = (int64_t)blockIdx.x * ppb + threadIdx.x / lpp;
+  if (pixi >= npix) return;
+  const int cq = (threadIdx.x % lpp) * 4;
+  const int bx = (int)(pixi % p.win);
+  const int64_t t = pixi / p.win;
+  const int a = (int)(t % p.hin), b = (int)(t / p.hin);
+  const int cw = p.win + 1, ch = p.hin + 1;
+  float kf[16];                                                        // upfirdn2d correlates with the flipped kernel
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = __ldg(fir + 15 - i);
+  const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+  const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
+  const float slope = p.act == E4S_ACT_LRELU ? p.act_slope : 1.f;
+  float nz[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.noise) {
+    const float* np = p.noise + (int64_t)b * p.noise_sb + (int64_t)(2 * a) * p.wout + 2 * bx;
+    nz[0] = nw * __ldg(np); nz[1] = nw * __ldg(np + 1); nz[2] = nw * __ldg(np + p.wout); nz[3] = nw * __ldg(np + p.wout + 1);
+  }
+  float* obase = p.out + (((int64_t)b * p.hout + 2 * a) * p.wout + 2 * bx) * p.out_pitch;
+  const float* zb[9];
+  bool ok[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int cy = a - 1 + i / 3, cx = bx - 1 + i % 3;
+    ok[i] = cy >= 0 && cx >= 0;                                        // cy <= H, cx <= W always exist; their out-of-grid phases hold 0
+    zb[i] = z + (((int64_t)b * ch + (ok[i] ? cy : 0)) * cw + (ok[i] ? cx : 0)) * 4 * p.cout;
+  }
+  for (int c = cq; c < p.cout; c += 4 * lpp) {
+    float4 zw[25];
+#pragma unroll
+    for (int wy = 0; wy < 5; ++wy) {
+#pragma unroll
+      for (int wx = 0; wx < 5; ++wx) {
+        const int ci = ((wy + 1) >> 1) * 3 + ((wx + 1) >> 1);          // window index -> cell index 0,1,1,2,2 ; phase 1,0,1,0,1
+        zw[wy * 5 + wx] = ldg4(zb[ci] + (((wy + 1) & 1) * 2 + ((wx + 1) & 1)) * p.cout + c);
+      }
+    }
+    float4 acc[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int wy = 0; wy < 5; ++wy) {
+#pragma unroll
+      for (int wx = 0; wx < 5; ++wx) {
+        const int ci = ((wy + 1) >> 1) * 3 + ((wx + 1) >> 1);
+        float4 zv = zw[wy * 5 + wx];
+        if (!ok[ci]) zv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int u = wy - dy, v = wx - dx;
+            if (u >= 0 && u < 4 && v >= 0 && v < 4) {
+              const float k = kf[u * 4 + v];
+              float4& ac = acc[dy * 2 + dx];
+              ac.x = fmaf(k, zv.x, ac.x); ac.y = fmaf(k, zv.y, ac.y); ac.z = fmaf(k, zv.z, ac.z); ac.w = fmaf(k, zv.w, ac.w);
+            }
+          }
+        }
+      }
+    }
+    const float4 add = p.ch_shift ? ldg4(p.ch_shift + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 dm = p.demod ? ldg4(p.demod + (int64_t)b * p.regions * p.cout + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float4 v4;
+      v4.x = fmaf(acc[o].x, dm.x, add.x + nz[o]); v4.y = fmaf(acc[o].y, dm.y, add.y + nz[o]);
+      v4.z = fmaf(acc[o].z, dm.z, add.z + nz[o]); v4.w = fmaf(acc[o].w, dm.w, add.w + nz[o]);
+      v4.x = (v4.x < 0.f ? v4.x * slope : v4.x) * gain; v4.y = (v4.y < 0.f ? v4.y * slope : v4.y) * gain;
+      v4.z = (v4.z < 0.f ? v4.z * slope : v4.z) * gain; v4.w = (v4.w < 0.f ? v4.w * slope : v4.w) * gain;
+      *reinterpret_cast<float4*>(obase + ((int64_t)(o >> 1) * p.wout + (o & 1)) * p.out_pitch + c) = v4;
+    }
+  }
+}
+
 // w [cout][cin][3][3] -> out [9][cin][cout_pad]: block i = scale * W[ky][kx] with ky*3 + kx = c_uz_order[i], as a [cin x cout] matrix
 __global__ void __launch_bounds__(256) pack_convt_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int cout_pad,
                                                                  float scale, int64_t total) {
@@ -600,35 +695,58 @@ extern "C" int e4s_upz_build_rows(const uint8_t* labels, int batch, int lab_h, i
   return check_launch("upz_build_rows");
 }
 
+template <int SW>
+static int launch_upz_gemm(const E4SConv* p, const void* w_packed9, const int32_t* rows, const int32_t* count, int max_rows, float* z, cudaStream_t s) {
+  static bool attr_set_dev[E4S_MAX_DEVICES] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_upz_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, UZ_SMEM);
+    if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc_upz: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(max_rows, TC_BM);
+  conv_tc_upz_kernel<SW><<<dim3((unsigned)tiles, (unsigned)(p->cout / SW)), UZ_THREADS, UZ_SMEM, s>>>(
+      *p, static_cast<const uint8_t*>(w_packed9), tc_block_n(p->cout), reinterpret_cast<const int2*>(rows), count, max_rows, z, g_uz_dbg);
+  return check_launch("e4s_conv_tc_upz(gemm)");
+}
+
 extern "C" int e4s_conv_tc_upz(const E4SConv* p, const void* w_packed9, const float* fir, const int32_t* cells, const int32_t* rows,
                                const int32_t* count, int max_rows, float* z, void* stream) {
-  E4S_REQUIRE(p && w_packed9 && fir && cells && rows && count && z && max_rows > 0, "conv_tc_upz: null argument");
+  E4S_REQUIRE(p && w_packed9 && fir && z && max_rows > 0, "conv_tc_upz: null argument");
   E4S_REQUIRE(p->mode == E4S_CONV_UP2_POLYPHASE && p->kh == 3 && p->kw == 3 && p->hout == 2 * p->hin && p->wout == 2 * p->win,
               "conv_tc_upz: needs the 3x3 up-convolution geometry");
-  E4S_REQUIRE(p->x && p->out && p->labels && p->smod && p->regions >= 1 && p->regions <= 32, "conv_tc_upz: needs x, out, labels, a style table and <= 32 regions");
-  E4S_REQUIRE(p->cin % 64 == 0 && p->cout % 128 == 0 && p->batch > 0, "conv_tc_upz: needs cin %% 64 == 0 and cout %% 128 == 0 (cin=%d cout=%d)", p->cin, p->cout);
+  const bool direct = p->labels == nullptr;              // un-masked layer: one row per cell in cell order, no list
+  if (direct) {
+    E4S_REQUIRE(!cells && !rows && !count && p->regions == 1 && (int64_t)max_rows == (int64_t)p->batch * (p->hin + 1) * (p->win + 1),
+                "conv_tc_upz: the direct (un-masked) form takes no row list, one style per sample and max_rows = batch*(hin+1)*(win+1)");
+    E4S_REQUIRE(p->cout == 32 || p->cout == 64 || p->cout % 128 == 0, "conv_tc_upz: the direct form needs cout in {32, 64, 128 n} (cout=%d)", p->cout);
+  } else {
+    E4S_REQUIRE(cells && rows && count && p->smod && p->regions >= 1 && p->regions <= 32, "conv_tc_upz: needs the row list, a style table and <= 32 regions");
+    E4S_REQUIRE(p->cout % 128 == 0, "conv_tc_upz: the regional form needs cout %% 128 == 0 (cout=%d)", p->cout);
+  }
+  E4S_REQUIRE(p->x && p->out && p->cin % 64 == 0 && p->batch > 0, "conv_tc_upz: needs x, out and cin %% 64 == 0 (cin=%d)", p->cin);
   E4S_REQUIRE(p->tc_fmt == E4S_TC_BF16 && !p->in_mean && !p->in_shift && !p->in_square && !p->rgb && !p->res && !p->pixw && !p->accumulate &&
                   !p->ch_scale && (!p->noise || p->noise_sc == 0) && (p->act == E4S_ACT_NONE || p->act == E4S_ACT_LRELU),
               "conv_tc_upz: unsupported operand format / prologue / epilogue option");
   E4S_REQUIRE(p->x_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->smod) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (!p->smod || (reinterpret_cast<uintptr_t>(p->smod) & 15) == 0) &&
                   (!p->demod || (reinterpret_cast<uintptr_t>(p->demod) & 15) == 0) && (!p->ch_shift || (reinterpret_cast<uintptr_t>(p->ch_shift) & 15) == 0) &&
                   (reinterpret_cast<uintptr_t>(w_packed9) & 15) == 0,
               "conv_tc_upz: pointers must be 16-byte aligned, pitches %% 4 == 0");
-  static bool attr_set_dev[E4S_MAX_DEVICES] = {};
-  bool& attr_set = attr_set_dev[current_device_slot()];
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_upz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UZ_SMEM);
-    if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc_upz: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   cudaStream_t s = as_stream(stream);
-  const int tiles = ceil_div(max_rows, TC_BM);
-  const int bn = tc_block_n(p->cout);
-  conv_tc_upz_kernel<<<dim3((unsigned)tiles, (unsigned)(p->cout / 128)), UZ_THREADS, UZ_SMEM, s>>>(*p, static_cast<const uint8_t*>(w_packed9), bn,
-                                                                                                 reinterpret_cast<const int2*>(rows), count, max_rows, z, g_uz_dbg);
-  int rc = check_launch("e4s_conv_tc_upz(gemm)");
+  int rc;
+  if (p->cout == 32) rc = launch_upz_gemm<32>(p, w_packed9, rows, count, max_rows, z, s);
+  else if (p->cout == 64) rc = launch_upz_gemm<64>(p, w_packed9, rows, count, max_rows, z, s);
+  else rc = launch_upz_gemm<128>(p, w_packed9, rows, count, max_rows, z, s);
   if (rc) return rc;
+  if (direct) {
+    const int lpp = (p->cout < 128 ? p->cout : 128) / 4;
+    const int64_t npix = (int64_t)p->batch * p->hin * p->win;
+    const int64_t blocks = ceil_div64(npix, 256 / lpp);
+    E4S_REQUIRE(blocks < 0x7fffffff, "conv_tc_upz: too many pixels");
+    upz_blur_direct_kernel<<<(unsigned)blocks, 256, 0, s>>>(*p, z, fir, lpp, npix);
+    return check_launch("e4s_conv_tc_upz(blur direct)");
+  }
   const int64_t patches = (int64_t)p->batch * ((p->hin + 7) / 8) * ((p->win + 7) / 8);
   E4S_REQUIRE(patches < 0x7fffffff, "conv_tc_upz: too many output patches");
   upz_blur_kernel<<<dim3((unsigned)patches, (unsigned)(p->cout / 64)), 256, 0, s>>>(*p, z, reinterpret_cast<const int2*>(cells), count, max_rows, fir);

@@ -65,6 +65,73 @@ __global__ void chan_stats_final_kernel(const double2* __restrict__ partial, int
   if (rstd) rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// The same statistics in ONE launch when the tensor allows 16-byte loads (c % 4 == 0, pitch % 4 == 0): each thread streams four channels
+// (float4 per pixel, 32 pixel rows per block pass), the block writes its slice's partial sums, and the LAST block of a (sample, 32-channel
+// group) to arrive -- a ticket counter in the first 64 KB of the workspace, which must be zero when the call starts and is zero again when
+// it ends -- reduces the slices in index order and writes mean / rstd.  The result does not depend on which block happens to be last.
+constexpr int STATS_CNT_BYTES = 65536;
+__global__ void __launch_bounds__(256) chan_stats_fused_kernel(const float* __restrict__ x, int64_t pitch, int hw, int c, int split, int batch, float eps,
+                                                               double2* __restrict__ partial, int* __restrict__ counters, float* __restrict__ mean,
+                                                               float* __restrict__ rstd) {
+  __shared__ double red[32][8][8];                         // [pixel row][4-channel group][sum x4 | sumsq x4]
+  __shared__ int s_last;
+  const int cq = threadIdx.x & 7, py = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 32, sl = blockIdx.y, b = blockIdx.z;
+  const int per = (hw + split - 1) / split;
+  const int p0 = sl * per, p1 = min(hw, p0 + per);
+  const int ch = c0 + cq * 4;
+  double sm[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+  if (ch < c) {
+    const float* xp = x + (int64_t)b * hw * pitch + ch;
+#pragma unroll 4
+    for (int p = p0 + py; p < p1; p += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (int64_t)p * pitch));
+      sm[0] += (double)v.x; sq[0] += (double)v.x * (double)v.x;
+      sm[1] += (double)v.y; sq[1] += (double)v.y * (double)v.y;
+      sm[2] += (double)v.z; sq[2] += (double)v.z * (double)v.z;
+      sm[3] += (double)v.w; sq[3] += (double)v.w * (double)v.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[py][cq][j] = sm[j];
+    red[py][cq][4 + j] = sq[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && c0 + threadIdx.x < c) {
+    const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+    double a = 0.0, q = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      a += red[r][g][j];
+      q += red[r][g][4 + j];
+    }
+    partial[((int64_t)b * split + sl) * c + c0 + threadIdx.x] = make_double2(a, q);
+  }
+  __threadfence();
+  __syncthreads();
+  int* cnt = counters + (int64_t)b * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) s_last = atomicAdd(cnt, 1) == split - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 32 && c0 + threadIdx.x < c) {
+    const int chn = c0 + threadIdx.x;
+    double a = 0.0, q = 0.0;
+    for (int k = 0; k < split; ++k) {
+      const double2 v = __ldcg(&partial[((int64_t)b * split + k) * c + chn]);
+      a += v.x;
+      q += v.y;
+    }
+    const double m = a / hw;
+    double var = q / hw - m * m;
+    if (var < 0.0) var = 0.0;
+    if (mean) mean[(int64_t)b * c + chn] = (float)m;
+    if (rstd) rstd[(int64_t)b * c + chn] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  if (threadIdx.x == 0) *cnt = 0;
+}
+
 // one warp per output feature
 __global__ void __launch_bounds__(256) vec_fc_kernel(const float* __restrict__ x, int64_t x_stride,
                                                      const float* __restrict__ w, const float* __restrict__ scale,
@@ -353,7 +420,7 @@ static inline unsigned grid_for(int64_t n, int block) {
 using namespace e4s;
 
 extern "C" int64_t e4s_chan_stats_ws_bytes(int batch, int c) {
-  return (int64_t)batch * STATS_MAX_SPLIT * c * (int64_t)sizeof(double2);
+  return STATS_CNT_BYTES + (int64_t)batch * STATS_MAX_SPLIT * c * (int64_t)sizeof(double2);
 }
 
 extern "C" int e4s_chan_stats_f32(const float* x, int64_t x_pitch, int batch, int hw, int c, float eps, float* mean,
@@ -363,11 +430,15 @@ extern "C" int e4s_chan_stats_f32(const float* x, int64_t x_pitch, int batch, in
   E4S_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "chan_stats: workspace must be 16-byte aligned");
   const int split = stats_split(batch, hw, c);
   dim3 grid(ceil_div(c, 32), split, batch);
-  chan_stats_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_pitch, hw, c, split, reinterpret_cast<double2*>(ws));
+  double2* partial = reinterpret_cast<double2*>(static_cast<uint8_t*>(ws) + STATS_CNT_BYTES);
+  if (c % 4 == 0 && x_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (int64_t)batch * grid.x * 4 <= STATS_CNT_BYTES) {
+    chan_stats_fused_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_pitch, hw, c, split, batch, eps, partial, static_cast<int*>(ws), mean, rstd);
+    return check_launch("chan_stats_fused");
+  }
+  chan_stats_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_pitch, hw, c, split, partial);
   int rc = check_launch("chan_stats_partial");
   if (rc) return rc;
-  chan_stats_final_kernel<<<ceil_div(batch * c, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const double2*>(ws), batch,
-                                                                                   hw, c, split, eps, mean, rstd);
+  chan_stats_final_kernel<<<ceil_div(batch * c, 256), 256, 0, as_stream(stream)>>>(partial, batch, hw, c, split, eps, mean, rstd);
   return check_launch("chan_stats_final");
 }
 

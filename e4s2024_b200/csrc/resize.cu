@@ -156,6 +156,65 @@ __global__ void bicubic_h_norm_kernel(const float* __restrict__ tmp, int ho, int
   }
 }
 
+// Both passes in one kernel (factor <= 4): a block produces a 16 x 32 tile of output pixels for the three channels from a shared-memory
+// copy of the (16f + 3f) x (32f + 3f) input window (reflect padding applied while loading).  Same arithmetic as the two kernels above --
+// vertical fmaf chain over the taps in order, then the horizontal one, clamp, normalise -- so the results are bit-identical; what is
+// saved is the [planes, h/f, w] intermediate in HBM (written and read back) and the strided 4-byte NHWC stores: pixels leave as whole
+// c_pad-channel rows.
+constexpr int BC_TY = 16, BC_TX = 32;
+__global__ void __launch_bounds__(256) bicubic_fused_kernel(const float* __restrict__ x, int hin, int win, int factor, const float* __restrict__ taps,
+                                                           const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ y,
+                                                           int c_pad, int do_clamp) {
+  extern __shared__ float bsm[];
+  const int n = factor * 4, pad0 = (n - factor) / 2, ho = hin / factor, wo = win / factor;
+  const int rows = BC_TY * factor + n - factor, cols = BC_TX * factor + n - factor;
+  float* sin_ = bsm;                                  // [rows][cols]
+  float* sv = sin_ + rows * cols;                     // [BC_TY][cols]
+  float* so = sv + BC_TY * cols;                      // [BC_TY][BC_TX][4]: channels 0..2 (+ one zero)
+  float* stap = so + BC_TY * BC_TX * 4;               // [n]
+  const int b = blockIdx.z, oy0 = blockIdx.y * BC_TY, ox0 = blockIdx.x * BC_TX;
+  const int tid = threadIdx.x;
+  if (tid < n) stap[tid] = __ldg(taps + tid);
+  for (int ch = 0; ch < 3; ++ch) {
+    const float* xp = x + ((int64_t)b * 3 + ch) * hin * win;
+    __syncthreads();                                  // previous channel's readers are done (also publishes stap)
+    for (int i = tid; i < rows * cols; i += 256) {
+      const int r = i / cols, c = i - r * cols;
+      // partial tiles at the bottom / right edge read rows past the reflection range: clamp (those outputs are never stored)
+      const int iy = min(max(reflect_idx(oy0 * factor + r - pad0, hin), 0), hin - 1), ix = min(max(reflect_idx(ox0 * factor + c - pad0, win), 0), win - 1);
+      sin_[i] = __ldg(xp + (int64_t)iy * win + ix);
+    }
+    __syncthreads();
+    for (int i = tid; i < BC_TY * cols; i += 256) {
+      const int ty = i / cols, c = i - ty * cols;
+      float v = 0.f;
+      for (int k = 0; k < n; ++k) v = fmaf(sin_[(ty * factor + k) * cols + c], stap[k], v);
+      sv[i] = v;
+    }
+    __syncthreads();
+    const float m = __ldg(mean + ch), sd = __ldg(stdv + ch);
+    for (int i = tid; i < BC_TY * BC_TX; i += 256) {
+      const int ty = i / BC_TX, tx = i - ty * BC_TX;
+      float v = 0.f;
+      for (int k = 0; k < n; ++k) v = fmaf(sv[ty * cols + tx * factor + k], stap[k], v);
+      if (do_clamp) v = fminf(fmaxf(v, 0.f), 1.f);
+      so[i * 4 + ch] = (v - m) / sd;
+    }
+  }
+  __syncthreads();
+  // NHWC rows of c_pad floats (c_pad % 4 == 0): first float4 = (c0, c1, c2, 0), the rest zero
+  const int q4 = c_pad >> 2;
+  for (int i = tid; i < BC_TY * BC_TX * q4; i += 256) {
+    const int q = i % q4, px = i / q4;
+    const int ty = px / BC_TX, tx = px - ty * BC_TX;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy >= ho || ox >= wo) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q == 0) v = make_float4(so[px * 4], so[px * 4 + 1], so[px * 4 + 2], 0.f);
+    *reinterpret_cast<float4*>(y + (((int64_t)b * ho + oy) * wo + ox) * c_pad + 4 * q) = v;
+  }
+}
+
 static inline unsigned grid_for(int64_t n, int block) {
   int64_t g = ceil_div64(n, block);
   const int64_t cap = 148 * 64;
@@ -204,6 +263,20 @@ extern "C" int e4s_bicubic_down_norm_f32(const float* x, int batch, int hin, int
   E4S_REQUIRE(batch > 0 && factor >= 1 && hin % factor == 0 && win % factor == 0 && c_pad >= 3, "bicubic: bad shape");
   E4S_REQUIRE(hin > 4 * factor && win > 4 * factor, "bicubic: image too small for reflect padding");
   const int ho = hin / factor, wo = win / factor;
+  if (factor <= 4 && c_pad % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const int n = factor * 4, rows = BC_TY * factor + n - factor, cols = BC_TX * factor + n - factor;
+    const size_t smem = (size_t)(rows * cols + BC_TY * cols + BC_TY * BC_TX * 4 + n) * sizeof(float);
+    static bool attr_dev[E4S_MAX_DEVICES] = {};
+    bool& attr = attr_dev[current_device_slot()];
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(bicubic_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr = true;
+    }
+    bicubic_fused_kernel<<<dim3((unsigned)ceil_div(wo, BC_TX), (unsigned)ceil_div(ho, BC_TY), (unsigned)batch), 256, smem, as_stream(stream)>>>(
+        x, hin, win, factor, taps, mean, stdv, y, c_pad, do_clamp);
+    return check_launch("bicubic_fused");
+  }
   int64_t t1 = (int64_t)batch * 3 * ho * win;
   bicubic_v_kernel<<<grid_for(t1, 256), 256, 0, as_stream(stream)>>>(x, hin, win, factor, taps, tmp, t1);
   int rc = check_launch("bicubic_v");

@@ -104,9 +104,19 @@ def wide_eligible(cin: int, cout: int, hin: int, win: int, up2: bool) -> bool:
 WIDE_OVER_REGION_JOBS = float(os.environ.get("E4S_WIDE_RATIO", "1.25"))
 
 
-def upz_eligible(cin: int, cout: int) -> bool:
-    """Mirror of e4s_conv_tc_upz's shape check: masked up-convolutions that can run as the (cell, region) conv_transpose GEMM."""
-    return _ENGINE == "tc" and os.environ.get("E4S_UPZ", "1") != "0" and cin % 64 == 0 and cout % 128 == 0 and tc_available()
+def upz_eligible(cin: int, cout: int, regional: bool = True) -> bool:
+    """Mirror of e4s_conv_tc_upz's shape check: up-convolutions that can run as the conv_transpose cell GEMM + FIR pass --
+    regional (masked) layers over (cell, region) rows, un-masked layers in the direct form (one row per cell, also cout 32 / 64)."""
+    if _ENGINE != "tc" or os.environ.get("E4S_UPZ", "1") == "0" or cin % 64 or not tc_available():
+        return False
+    if regional:
+        return cout % 128 == 0
+    # Off by default: measured on B200 (tests/micro/upz_direct_time.py, profiles/r2_upz_direct.txt) the direct form LOSES on the un-masked
+    # 512^2 / 1024^2 layers -- 2.5 vs 1.3 ms and 5.1 vs 2.0 ms against the poly-phase halo kernel.  With cin = 128 / 64 a 128-row tile has one
+    # or two 64-channel groups of MMAs, so the one-tile-per-CTA kernel is all prologue / epilogue (10 us per tile), and the Z round trip
+    # through HBM (2 x 2.1 GB at 1024^2) costs more than the 4x MMAs it saves.  It would take the halo kernel's persistent, overlapped
+    # structure with the FIR applied in its epilogue to win here.
+    return os.environ.get("E4S_UPZ_DIRECT", "0") == "1" and (cout in (32, 64) or cout % 128 == 0)
 
 
 # run the (cell, region) form while it has at most this many rows per cell (its MMA work is rows x 9 against cells x 36 -- x72 on tiles
@@ -165,7 +175,7 @@ def pack_up_weight(w: torch.Tensor, fir: torch.Tensor, want_tc: bool = True, sca
     wf, ff = w.detach().contiguous().float(), fir.detach().contiguous().float().to(w.device)
     m = L.pack_upconv_weights(wf, ff, pad_to(co, 4), scale)
     pc = _finish_pack(m, ci, co, 3, 3, 4, want_tc)
-    if pc.tc is not None and upz_eligible(ci, co):
+    if pc.tc is not None and (upz_eligible(ci, co, True) or upz_eligible(ci, co, False)):
         m9 = L.pack_convt_weights(wf, pad_to(co, 4), scale)
         pc.tc9 = L.pack_weights_tc(m9, 9, ci, ci, co, pad_to(co, 4))
         pc.fir = ff
@@ -280,9 +290,11 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
     eng = engine or _ENGINE
     use_tc = eng == "tc" and pw.tc is not None
     use_rj = use_tc and region_jobs is not None and labels is not None
-    use_upz = use_tc and upz is not None and labels is not None and up2 and pw.tc9 is not None and \
-        (noise is None or noise.shape[1] == 1) and ch_scale is None and res is None and pixw is None and not accumulate and \
-        act in (L.ACT_NONE, L.ACT_LRELU) and in_stats is None and rgb is None
+    upz_epi_ok = (noise is None or noise.shape[1] == 1) and ch_scale is None and res is None and pixw is None and not accumulate and \
+        act in (L.ACT_NONE, L.ACT_LRELU) and in_stats is None and rgb is None and pw.tc9 is not None and up2 and use_tc and in_shift == 0
+    use_upz = upz_epi_ok and upz is not None and labels is not None and upz_eligible(pw.cin, pw.cout, True)
+    # un-masked up-convolution (one style per sample): the same cell GEMM without a row list
+    use_upz_direct = upz_epi_ok and labels is None and regions == 1 and demod_off == 0 and smod_off == 0 and upz_eligible(pw.cin, pw.cout, False)
     if use_tc:
         p.tc_fmt, p.tc_out_scale = pw.tc_fmt, pw.tc_out_scale
         if TC_UNBIAS_OVERRIDE is not None:
@@ -293,7 +305,11 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
         L.conv_upz(p, pw.tc9, pw.fir, upz.cells, upz.rows, upz.count_dev, upz.max_rows, z)
 
     def launch():
-        if use_upz and upz.count is None:
+        if use_upz_direct:
+            n_cells = b * (hin + 1) * (win + 1)
+            z = torch.empty(n_cells * 4 * pw.cout, device=x.t.device, dtype=torch.float32)
+            L.conv_upz(p, pw.tc9, pw.fir, None, None, None, n_cells, z)
+        elif use_upz and upz.count is None:
             # lazy region context: the row count on the device runs either the (cell, region) form or the poly-phase kernel
             p.pred_count, p.pred_limit = upz.count_dev.data_ptr(), upz.limit
             p.pred_run_if_gt = 0

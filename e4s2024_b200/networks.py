@@ -70,6 +70,7 @@ class Net3(nn.Module):
             p.requires_grad = False
         self._bias_cache = None
         E.install_pack_invalidation(self)
+        self.eval()          # like Generator: train() is the explicit switch to the differentiable (PTI) path
 
     # ---- encoder --------------------------------------------------------------------------------
     def _encode(self, img, mask):

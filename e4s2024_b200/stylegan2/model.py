@@ -398,6 +398,9 @@ class Generator(nn.Module):
             in_channel = out_channel
         self.n_latent = self.log_size * 2 - 2
         E.install_pack_invalidation(self)
+        # The drop-in is constructed in eval() mode (every pipeline of the reference calls .eval() on the loaded network anyway): train()
+        # is the explicit switch to the differentiable path, so a caller that merely forgot eval() / no_grad() does not pay for autograd.
+        self.eval()
 
     def _region_job_keys(self):
         """(hout, wout, up2) of the masked StyledConv layers whose geometry the halo kernel takes."""
@@ -405,7 +408,7 @@ class Generator(nn.Module):
         res = 4
         for conv_up, conv2 in zip(self.convs[::2], self.convs[1::2]):
             res *= 2
-            if conv_up.mask_op and not E.upz_eligible(conv_up.conv.in_channel, conv_up.conv.out_channel) and \
+            if conv_up.mask_op and not E.upz_eligible(conv_up.conv.in_channel, conv_up.conv.out_channel, True) and \
                     E.halo_geometry_ok(conv_up.conv.in_channel, conv_up.conv.out_channel, res // 2, res // 2, True):
                 keys.append((res, res, True))
             if conv2.mask_op and E.halo_geometry_ok(conv2.conv.in_channel, conv2.conv.out_channel, res, res, False):

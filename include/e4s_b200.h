@@ -151,7 +151,9 @@ int e4s_region_tile_jobs(const uint8_t* labels, int batch, int lab_h, int lab_w,
  * e4s_pack_convt_weights_f32: w [cout][cin][3][3] -> out [9][cin][cout_pad] (the 9 taps as [cin x cout] matrices in the order the kernel
  *   consumes them), to be packed with e4s_pack_weights_tc(out, phases = 9, k = cin, cin, cout, cout_pad).
  * e4s_conv_tc_upz: p as for e4s_conv_tc with mode E4S_CONV_UP2_POLYPHASE, labels, smod (cin % 64 == 0, cout % 128 == 0, bf16 split,
- *   single-channel noise, NONE / LRELU); fir = the 4x4 blur kernel (Blur(pad=(1,1)), already x4); z: scratch of max_rows*4*cout floats. */
+ *   single-channel noise, NONE / LRELU); fir = the 4x4 blur kernel (Blur(pad=(1,1)), already x4); z: scratch of max_rows*4*cout floats.
+ *   Un-masked layers (labels == NULL, regions == 1; cout in {32, 64, 128 n}): DIRECT form, cells = rows = count = NULL and
+ *   max_rows = batch*(hin+1)*(win+1) -- row i is cell i, no list is built. */
 int e4s_upz_build_rows(const uint8_t* labels, int batch, int lab_h, int lab_w, int hin, int win, int32_t* cells, int32_t* rows,
                        int32_t* count, int max_rows, void* stream);
 int e4s_pack_convt_weights_f32(const float* w, float* out, int cout, int cin, int cout_pad, float scale, void* stream);
@@ -220,7 +222,9 @@ int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, int w, int 
                   const float* bias, const float* skip, const float* fir, float* rgb, int accumulate, void* stream);
 
 /* per-(b,c) statistics of an NHWC tensor: mean, rstd = 1/sqrt(var_biased + eps) (either may be NULL).
- * ws: workspace of e4s_chan_stats_ws_bytes(batch, c) bytes. Deterministic (fixed split, fp64 partials). */
+ * ws: workspace of e4s_chan_stats_ws_bytes(batch, c) bytes whose first 64 KB (arrival counters of the single-launch form) must be ZERO
+ * when the call starts; the call leaves them zero again, so one zero-filled buffer serves any number of calls on a stream.
+ * Deterministic (fixed split, fp64 partials, slices reduced in index order). */
 int64_t e4s_chan_stats_ws_bytes(int batch, int c);
 int e4s_chan_stats_f32(const float* x, int64_t x_pitch, int batch, int hw, int c, float eps, float* mean, float* rstd,
                        void* ws, void* stream);

@@ -249,3 +249,38 @@ def test_upz_row_list_is_the_set_of_regions_reading_each_cell():
                     assert int(rows[base + j, 0]) == (b << 8 | r) and int(rows[base + j, 1]) == (cy << 16 | cx)
                 total += len(want)
     assert total == uz.count
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 32, 20, 12), (128, 64, 16, 16), (64, 128, 8, 24)])
+def test_upz_direct_form_matches_the_polyphase_kernels(cin, cout, H, W, monkeypatch):
+    """The direct (un-masked) form of e4s_conv_tc_upz -- opt-in, E4S_UPZ_DIRECT=1: one row per cell, slot widths 32 / 64 / 128 -- against the
+    exact-fp32 poly-phase engine.  (It is off by default because it is slower on B200, see engine.upz_eligible.)"""
+    from e4s2024_b200 import _lib as L
+    from e4s2024_b200 import engine as E
+    if not E.tc_available():
+        pytest.skip("library built without the tcgen05 engine")
+    monkeypatch.setenv("E4S_UPZ_DIRECT", "1")
+    name = f"upzd_{cin}_{cout}"
+    B = 2
+    x = _mk((B, H, W, cin), name + ".x")
+    w = _mk((cout, cin, 3, 3), name + ".w", (1.0 / (cin * 9)) ** 0.5)
+    smod = (1.0 + 0.3 * _mk((B, 1, cin), name + ".s")).contiguous()
+    demod = (1.0 + 0.2 * _mk((B, 1, cout), name + ".d")).contiguous()
+    noise = _mk((1, 1, 2 * H, 2 * W), name + ".n")
+    nw = torch.tensor([0.1], device="cuda")
+    bias = _mk((cout,), name + ".b", 0.1)
+    fir = torch.tensor([1., 3., 3., 1.])
+    fir = (torch.outer(fir, fir) / 64 * 4).cuda()
+    pw = E.pack_up_weight(w, fir)
+    assert pw.tc9 is not None
+    kw = dict(up2=True, smod=smod, demod=demod, regions=1, noise=noise, noise_w=nw, ch_shift=bias, act=L.ACT_LRELU, slope=0.2, gain=2 ** 0.5)
+    y32 = E.conv(E.View(x), pw, engine="f32", **kw).t
+    launches = L.launch_count()
+    yd = E.conv(E.View(x), pw, engine="tc", **kw).t
+    assert L.launch_count() - launches == 2                     # cell GEMM + FIR pass
+    monkeypatch.setenv("E4S_UPZ_DIRECT", "0")
+    yh = E.conv(E.View(x), pw, engine="tc", **kw).t
+    torch.cuda.synchronize()
+    scale = float(y32.abs().max())
+    assert float((yd - y32).abs().max()) < 2e-4 * max(scale, 1.0)
+    assert float((yh - y32).abs().max()) < 2e-4 * max(scale, 1.0)
