@@ -344,6 +344,13 @@ def other_configs(hot, dev, steps=3):
     ms, _ = time_steps(lambda: hot.parser.seg.labels(x, (512, 512), None), steps, warmup=2)
     res["bisenet_b64"] = {"workload": "configs[3]: BiSeNet forward batch=64 512x512 -> 19-class label map (x8 upsample + argmax fused), inputs resident",
                           "value": 64 / ms * 1e3, "unit": "faces/s", "ms_per_step": ms, "alg_tflops": 64 / ms * ALG_GFLOP["parse"]}
+    del x
+    torch.cuda.empty_cache()
+    # the reference pipelines call the path with ONE face at a time (face_swap_video_pipeline.py): latency of the whole hot path at batch 1
+    u8 = synth.smooth_image_u8("lat.img", 1, SIZE, 19).to(dev)
+    ms, _ = time_steps(lambda: hot.run_shard_u8(u8), max(steps, 5), warmup=3)
+    res["latency_b1"] = {"workload": "the full swap hot path on one uint8 1024^2 face (batch 1, inputs resident): what a frame-by-frame pipeline sees",
+                         "ms": ms, "value": 1e3 / ms, "unit": "faces/s"}
     return res
 
 
