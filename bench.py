@@ -351,6 +351,14 @@ def other_configs(hot, dev, steps=3):
     ms, _ = time_steps(lambda: hot.run_shard_u8(u8), max(steps, 5), warmup=3)
     res["latency_b1"] = {"workload": "the full swap hot path on one uint8 1024^2 face (batch 1, inputs resident): what a frame-by-frame pipeline sees",
                          "ms": ms, "value": 1e3 / ms, "unit": "faces/s"}
+    try:                                          # the same call replayed as one CUDA graph (serving.GraphedSwapPath): no host launch cost
+        from e4s2024_b200.serving import GraphedSwapPath
+        gs = GraphedSwapPath(hot, batch=1, size=SIZE)
+        ms_g, _ = time_steps(lambda: gs(u8), max(steps, 5), warmup=3)
+        res["latency_b1"]["ms_cuda_graph"] = ms_g
+        del gs
+    except Exception as e:
+        res["latency_b1"]["ms_cuda_graph"] = f"{type(e).__name__}: {e}"
     return res
 
 

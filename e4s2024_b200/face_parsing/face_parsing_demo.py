@@ -76,7 +76,13 @@ class FaceParser(nn.Module):
         self.seg.eval()
 
     def _consts(self, dev):
-        return (self.downsample.taps.to(dev), seg_mean.reshape(3).to(dev), seg_std.reshape(3).to(dev))
+        """Filter taps / normalisation constants on `dev`, uploaded once per device (three tiny H2D copies per call otherwise, which also
+        cannot be captured into a CUDA graph)."""
+        cache = self.__dict__.setdefault("_const_cache", {})
+        key = str(dev)
+        if key not in cache:
+            cache[key] = (self.downsample.taps.to(dev), seg_mean.reshape(3).to(dev), seg_std.reshape(3).to(dev))
+        return cache[key]
 
     def preprocess_tensor(self, im01: torch.Tensor) -> torch.Tensor:
         """[B,3,S,S] in [0,1] on the GPU, S >= 512 -> normalised NHWC [B,S/f,S/f,RGB_PAD] with the FIXED factor f = self.size // 512

@@ -138,3 +138,48 @@ class GraphedGenerator:
         torch.cuda.current_stream(self.latent.device).synchronize()
         return int(self.flag[0]) == 0
 
+
+
+class GraphedSwapPath:
+    """One CUDA graph of the whole hot path for a fixed batch: uint8 HWC images in -> (uint8 HWC images, u8 label maps) out
+    (`sharding.SwapHotPath.run_shard_u8`: TO_TENSOR / NORMALIZE, bicubic + BiSeNet + argmax / LUT, one-hot, encoder, LocalMLPs, generator,
+    tensor2im) -- ~250 kernel launches replayed as ONE launch from the host.  The reference pipelines call the path frame by frame
+    (batch 1), where the step is bound by the host's launch rate, not by the GPU.  Possible because the path contains no host wait: every
+    data-dependent choice (region jobs, rows per cell) is a device-side launch predicate, and the mask comes from the parser's own label
+    map, so it is one-hot by construction.
+
+        gs = GraphedSwapPath(hot, batch=1)
+        img_u8, labels = gs(frame_u8)        # the graph's static output buffers: consume (or copy) them before the next call
+    """
+
+    def __init__(self, hot, batch: int = 1, size: int = 1024, device: Optional[torch.device] = None, warmup: int = 2):
+        dev = device or next(hot.net.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedSwapPath needs a CUDA device (there is no CPU path)")
+        if hot.net.training:
+            raise RuntimeError("GraphedSwapPath captures the inference path: call net.eval() first")
+        self.hot = hot
+        self.inp = torch.zeros(batch, size, size, 3, dtype=torch.uint8, device=dev)
+        self.flag = torch.zeros(16, dtype=torch.int32).pin_memory()
+        G = hot.net.G
+        G._capture_host_flag = self.flag          # no event wait / host read inside the forward (Generator._forward)
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                            # warm-up off the default stream: packs weights, sets attributes, sizes workspaces
+                for _ in range(warmup):
+                    hot.run_shard_u8(self.inp)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.image, self.labels = hot.run_shard_u8(self.inp)
+        finally:
+            G._capture_host_flag = None
+
+    def __call__(self, img_u8: torch.Tensor):
+        if tuple(img_u8.shape) != tuple(self.inp.shape) or img_u8.dtype != torch.uint8:
+            raise ValueError(f"GraphedSwapPath was captured for uint8 images of shape {tuple(self.inp.shape)}, got {img_u8.dtype} {tuple(img_u8.shape)}")
+        self.inp.copy_(img_u8, non_blocking=True)
+        self.graph.replay()
+        return self.image, self.labels

@@ -123,7 +123,8 @@ class ModConvFn(Function):
         else:
             wt = w0.permute(1, 0, 2, 3).flip(2, 3).contiguous()                    # conv^T: flipped taps
         pwt = E.pack_conv_weight(wt, cin_pad=_r8(cout), scale=mc.scale)
-        present = [0] if labels is None else [int(v) for v in torch.unique(labels).tolist()]
+        # regions that occur in the mask (one host read per forward, cached on the label tensor by generator_forward)
+        present = [0] if labels is None else (getattr(labels, "_e4s_present", None) or [int(v) for v in torch.unique(labels).tolist()])
         dx = torch.empty(b, hin, win, cin, device=x.device, dtype=torch.float32)
         dw = torch.empty(cout, cin, k, k, device=x.device, dtype=torch.float32)
         ds = torch.zeros(b, regions, cin, device=x.device, dtype=torch.float32)
@@ -191,6 +192,7 @@ def generator_forward(G, latent: torch.Tensor, mask: torch.Tensor, noise, struct
     if not ctx.onehot:
         raise L.E4SError("the differentiable path needs one-hot masks (soft / overlapping masks are inference-only)")
     labels = ctx.labels
+    labels._e4s_present = [int(v) for v in torch.unique(labels).tolist()]      # read once here instead of once per layer in the backward
 
     def regional(i):
         return latent[:, :, i].reshape(b * k, sd), k

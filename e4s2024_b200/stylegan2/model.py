@@ -486,6 +486,8 @@ class Generator(nn.Module):
             raise L.E4SError(f"latent shape {tuple(latent.shape)} incompatible with n_latent={self.n_latent}")
         # lazy region context: no device->host read while the layers are being enqueued (the one-hot assumption is checked
         # after the last launch; a soft / overlapping mask re-runs the forward on the generic per-region path)
+        if _host_flag is None:
+            _host_flag = getattr(self, "_capture_host_flag", None)      # set by serving.GraphedSwapPath while it captures / replays
         ctx = _ctx if _ctx is not None else E.RegionCtx(mask.to(latent.device), self._region_job_keys(), lazy=True, host_flag=_host_flag,
                                                               upz_keys=self._upz_keys())
         if ctx.k != k or ctx.mask.shape[0] != b:

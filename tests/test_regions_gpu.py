@@ -105,3 +105,39 @@ def test_skinny_batched_linear_matches_fp64_and_is_batch_invariant():
         assert float((y.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
         outs[rows] = y.cpu()
     assert torch.equal(outs[1][0], outs[16][0]) and torch.equal(outs[16][5], outs[37][5])
+
+
+def test_fused_bicubic_is_bit_identical_to_the_two_pass_kernels():
+    """e4s_bicubic_down_norm_f32: the single-kernel form (shared-memory tile, c_pad % 4 == 0) against the two-pass kernels it replaces
+    (reached with c_pad = 5): same fmaf chains in the same order -> identical floats, on a size whose last tiles are partial."""
+    from e4s2024_b200 import _lib as L
+    from oracle import e4s_oracle as orc
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, 176, 208, generator=g).cuda()
+    for factor in (2, 4):
+        taps = orc.bicubic_taps(factor).float().cuda()
+        mean = torch.tensor([0.485, 0.456, 0.406]).cuda()
+        std = torch.tensor([0.229, 0.224, 0.225]).cuda()
+        fused = L.bicubic_down_norm(x, factor, taps, mean, std, 8)
+        twopass = L.bicubic_down_norm(x, factor, taps, mean, std, 5)
+        assert torch.equal(fused[..., :3], twopass[..., :3])
+        assert float(fused[..., 3:].abs().max()) == 0.0 and float(twopass[..., 3:].abs().max()) == 0.0
+
+
+def test_single_launch_chan_stats_matches_the_two_kernel_form_and_fp64():
+    """e4s_chan_stats_f32: the one-launch form (c % 4 == 0; ticket counter, last block reduces) against the two-kernel form (c = 7 of the same
+    buffer) and torch fp64; repeated calls reuse the zero-restored counters of the workspace."""
+    from e4s2024_b200 import _lib as L
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(3, 40, 24, 8, generator=g) * 2 + 0.5).cuda()
+    ref_m = x.double().mean((1, 2))
+    ref_r = 1.0 / torch.sqrt(x.double().var((1, 2), unbiased=False) + 1e-5)
+    for _ in range(3):
+        m8, r8 = L.chan_stats(x, 8)
+        m7, r7 = L.chan_stats(x, 7)
+        assert float((m8.double() - ref_m).abs().max()) < 1e-6 and float((r8.double() / ref_r - 1).abs().max()) < 1e-6
+        assert float((m8[:, :7] - m7).abs().max()) < 1e-6 and float((r8[:, :7] / r7 - 1).abs().max()) < 1e-6
+    big = torch.randn(2, 256, 256, 64, generator=g).cuda()          # several slices per (sample, channel group)
+    mb, rb = L.chan_stats(big, 64)
+    assert float((mb.double() - big.double().mean((1, 2))).abs().max()) < 1e-6
+    assert float((rb.double() * torch.sqrt(big.double().var((1, 2), unbiased=False) + 1e-5) - 1).abs().max()) < 1e-6

@@ -58,3 +58,31 @@ def test_graphed_generator_bit_exact():
     assert gg.verify() is True
     with pytest.raises(ValueError):                                  # no silent broadcast of a batch-1 input into the static buffers
         gg(lat[:1], msk[:1])
+
+
+def test_graphed_swap_path_bit_exact():
+    """serving.GraphedSwapPath: the whole hot path (parse -> one-hot -> Net3 -> tensor2im) replayed as one CUDA graph gives the bytes of
+    the eager path, for the capture input and for new inputs (the region job / row lists are rebuilt on the device at every replay)."""
+    from e4s2024_b200 import synth
+    from e4s2024_b200.face_parsing.face_parsing_demo import FaceParser
+    from e4s2024_b200.networks import Net3
+    from e4s2024_b200.serving import GraphedSwapPath
+    from e4s2024_b200.sharding import SwapHotPath
+    from oracle.ref_shims import net3_opts
+    net = Net3(net3_opts(out_size=256, remaining_layer_idx=13))
+    synth.synth_module_weights(net, seed=9)
+    net = net.cuda().eval()
+    net.latent_avg = synth.randn("gs.latent_avg", (18, 512), 9, 0.1).cuda()
+    parser = FaceParser(seg_ckpt=None, size=1024, device="cuda")
+    synth.synth_module_weights(parser.seg, seed=10)
+    parser.seg.cuda()
+    hot = SwapHotPath(net, parser, 12)
+    gs = GraphedSwapPath(hot, batch=2)
+    for seed in (3, 4):
+        u8 = synth.smooth_image_u8("gs.img", 2, 1024, seed).cuda()
+        img_g, lab_g = gs(u8)
+        img_g, lab_g = img_g.clone(), lab_g.clone()
+        img_e, lab_e = hot.run_shard_u8(u8)
+        torch.cuda.synchronize()
+        assert torch.equal(lab_g, lab_e) and torch.equal(img_g, img_e)
+    assert int(gs.flag[0]) == 0
