@@ -139,8 +139,9 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_tc_wide_kernel(const E4SCo
     for (int i = 0; i < 4; ++i) {
       const WdRow rw = rows[r0 + 32 * i];
       rb[i] = rw.b;
-      ry[i] = rw.y - 1;               // input row of tap ky = 0 (3x3, pad 1; the poly-phase taps read the same window)
-      rx[i] = rw.x - 1;
+      const int st = UP ? 1 : p.stride;                               // same-resolution mode also takes the stride-2 3x3 convs (encoder)
+      ry[i] = rw.y * st - 1;          // input row of tap ky = 0 (3x3, pad 1; the poly-phase taps read the same window)
+      rx[i] = rw.x * st - 1;
       rr[i] = rw.r4;
     }
     float4 sreg[4][2];                // modulation of this thread's 8 channels per row: changes every 9 chunks (and per pass)
@@ -432,11 +433,14 @@ bool tc_wide_eligible(const E4SConv* p) {
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
   if (!tc_epi_is_fast(*p) || p->in_mean || p->in_shift || p->in_square || p->rgb || !p->out) return false;
   if (!(p->kh == 3 && p->kw == 3)) return false;
-  if (!up && !(p->stride == 1 && p->pad == 1)) return false;
+  if (!up && !((p->stride == 1 || p->stride == 2) && p->pad == 1)) return false;
   if (p->cin % 64) return false;
   const int gh = up ? p->hin : p->hout, gw = up ? p->win : p->wout;
   if (gh % 16 || gw % 8) return false;
   if (p->regions > 255) return false;
+  // stride 2: only with enough tiles to fill the machine (512 -> 512 @64^2 -> 32^2, B = 16: 0.35 -> 0.17 ms); a 32-tile launch is faster on
+  // the gather kernel, whose grid also splits the output channels
+  if (!up && p->stride == 2 && (int64_t)p->batch * (gh / 16) * (gw / 8) < 100) return false;
   return up ? (p->cout % 128 == 0) : (p->cout % 512 == 0);
 }
 
