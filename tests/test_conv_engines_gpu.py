@@ -46,8 +46,9 @@ CASES = [
     ("wide_up2_c64_n128_coarse", 2, 16, 16, 64, 128, 3, 1, True, -4),
     ("wide_c64_n512_regions", 1, 32, 16, 64, 512, 3, 1, False, 7),
     ("wide_c128_n1024", 1, 16, 8, 128, 1024, 3, 1, False, 1),
-    ("wide_s2_c64_n512", 2, 32, 32, 64, 512, 3, 2, False, 1),             # stride-2 3x3 (the encoder's down-sampling convs) on the wide kernel
-    ("wide_s2_c128_n512_regions", 1, 32, 16, 128, 512, 3, 2, False, 3),
+    # stride-2 3x3 (the encoder's down-sampling convs) on the wide kernel: taken from 100 output tiles up (4 x 4 x 8 = 128 here)
+    ("wide_s2_c64_n512", 4, 128, 128, 64, 512, 3, 2, False, 1),
+    ("wide_s2_c64_n512_regions", 4, 128, 128, 64, 512, 3, 2, False, 3),
 ]
 
 
