@@ -49,7 +49,7 @@ class E4SConv(C.Structure):
 
 
 EXPORTS = [
-    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_region_tile_jobs", "e4s_upz_build_rows", "e4s_pack_convt_weights_f32", "e4s_conv_tc_upz",
+    "e4s_last_error", "e4s_launch_count", "e4s_device_info", "e4s_sizeof_conv", "e4s_conv_f32", "e4s_conv_f32_batched", "e4s_conv_tc", "e4s_conv_tc_regions", "e4s_conv_tc_splitk_ws_bytes", "e4s_conv_tc_splitk", "e4s_region_tile_jobs", "e4s_upz_build_rows", "e4s_pack_convt_weights_f32", "e4s_conv_tc_upz",
     "e4s_debug_halo_trace", "e4s_debug_halo_flags", "e4s_debug_upz_flags", "e4s_pack_weights_tc_bytes", "e4s_pack_weights_tc", "e4s_pack_weights_tc_fmt", "e4s_pack_conv_weights_f32", "e4s_pack_upconv_weights_f32", "e4s_upfirdn2d_f32", "e4s_bias_act_f32",
     "e4s_bias_act_grad_f32",
     "e4s_noise_bias_act_nhwc_f32", "e4s_nchw_to_nhwc_f32", "e4s_nhwc_to_nchw_f32", "e4s_mask_labels",
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         _lib.e4s_pack_weights_tc_bytes.restype = C.c_int64
         _lib.e4s_masked_mean_ws_bytes.restype = C.c_int64
         _lib.e4s_conv_wgrad_ws_bytes.restype = C.c_int64
+        _lib.e4s_conv_tc_splitk_ws_bytes.restype = C.c_int64
         _lib.e4s_region_dot_ws_bytes.restype = C.c_int64
         if _lib.e4s_sizeof_conv() != C.sizeof(E4SConv):
             raise E4SError(f"struct E4SConv mismatch: C {_lib.e4s_sizeof_conv()} vs ctypes {C.sizeof(E4SConv)}")
@@ -131,6 +132,13 @@ def conv(params: E4SConv, tc_weights: Optional[torch.Tensor] = None):
         _check(lib().e4s_conv_tc(C.byref(params), C.c_void_p(tc_weights.data_ptr()), _stream()), "e4s_conv_tc")
     else:
         _check(lib().e4s_conv_f32(C.byref(params), _stream()), "e4s_conv_f32")
+
+
+def conv_splitk(params: E4SConv, tc_weights: torch.Tensor, ksplit: int):
+    """e4s_conv_tc_splitk: the partial-accumulator workspace is allocated here (torch's caching allocator) for the duration of the call."""
+    n = int(lib().e4s_conv_tc_splitk_ws_bytes(C.byref(params), int(ksplit)))
+    ws = torch.empty(n // 4, dtype=torch.float32, device=tc_weights.device)
+    _check(lib().e4s_conv_tc_splitk(C.byref(params), C.c_void_p(tc_weights.data_ptr()), int(ksplit), _fp(ws.data_ptr()), _stream()), "e4s_conv_tc_splitk")
 
 
 def conv_regions(params: E4SConv, tc_weights: torch.Tensor, jobs: torch.Tensor, count: torch.Tensor, count_host: int):

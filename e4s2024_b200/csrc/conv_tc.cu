@@ -30,8 +30,11 @@ struct TcRow {
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 template <int BN>
+// ksplit > 1 (split-K, same-resolution / strided layers only): blockIdx.z selects a slice of num_kc / ksplit K chunks and the CTA writes its
+// RAW partial accumulator to part[z][output pixel][cout]; e4s_conv_tc_splitk's second kernel adds the slices in index order and applies the
+// epilogue.  For the generator's 4^2-16^2 layers: a handful of CTAs walking 72 chunks each otherwise (0.17-0.2 ms of pure latency).
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p, const uint8_t* __restrict__ wpk, const int64_t m_total,
-                                                                  const int tile2d) {
+                                                                  const int tile2d, const int ksplit, float* __restrict__ part) {
   if (p.pred_count != nullptr && ((__ldg(p.pred_count) > p.pred_limit) != (p.pred_run_if_gt != 0))) return;   // device-side launch predicate (e4s_b200.h)
   constexpr int STAGES = tc_stages(BN);
   constexpr int B_BYTES = BN * TC_BK * 2;
@@ -52,10 +55,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   float* sv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + TC_BM * 16 + 256);   // [mul | add | slope] x BN: this CTA's channels
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int phase_id = blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
+  const int phase_id = ksplit > 1 ? 0 : (int)blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
   const int n_tile = blockIdx.y;
   const int K = p.kh * p.kw * p.cin;
-  const int num_kc = (K + TC_BK - 1) / TC_BK;   // K is zero-padded to a multiple of 64 in the packed weights
+  const int num_kc_all = (K + TC_BK - 1) / TC_BK;   // K is zero-padded to a multiple of 64 in the packed weights
+  const int num_kc = num_kc_all / ksplit;           // chunks of this CTA's K slice (the host makes ksplit divide the chunk count)
+  const int kc_base = ksplit > 1 ? (int)blockIdx.z * num_kc : 0;
   const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
 
   // ---- one-time setup ---------------------------------------------------------------------------
@@ -197,14 +202,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       }
     };
 
-    if (grp < num_kc) prefetch(grp);
+    if (grp < num_kc) prefetch(kc_base + grp);
     for (int kc = grp; kc < num_kc; kc += 2) {
       const int s = kc % STAGES;
       const uint32_t par = (kc / STAGES) & 1;
       mbar_wait(bar_empty + 8 * s, par ^ 1);
       uint8_t* a_hi = smem + s * STAGE_BYTES;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
-      const int ci = grouped ? (kc / ntaps) * 64 + cg * 8 : (kc * TC_BK + cg * 8) % p.cin;
+      const int kca = kc_base + kc;                 // absolute chunk index
+      const int ci = grouped ? (kca / ntaps) * 64 + cg * 8 : (kca * TC_BK + cg * 8) % p.cin;
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int row = r0 + 16 * i;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
       fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      if (kc + 2 < num_kc) prefetch(kc + 2);
+      if (kc + 2 < num_kc) prefetch(kc_base + kc + 2);
     }
 
     // =========================== epilogue ========================================================
@@ -262,6 +268,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     er.nw = p.noise ? __ldg(p.noise_w) : 0.f;
     er.nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
     er.nz = (er.nrow && p.noise_sc == 0) ? er.nw * __ldg(er.nrow) : 0.f;
+    if (ksplit > 1) {
+      // split-K: the raw accumulator of this K slice -> part[z][pixel][cout] (the reduction kernel applies un-bias, demodulation, epilogue)
+      float* prow = part + ((int64_t)blockIdx.z * m_total + pix) * p.cout + n_base;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+        float acc[16];
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + c0), acc);   // warp-collective
+        if (f16) {
+          float acc2[16];
+          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + half * (BN / 2) + c0), acc2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(acc2[j], 1.f / TC_LO_SCALE, acc[j]);
+        }
+        if (live) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            reinterpret_cast<float4*>(prow + c0)[qd] = make_float4(acc[4 * qd], acc[4 * qd + 1], acc[4 * qd + 2], acc[4 * qd + 3]);
+        }
+      }
+    } else {
     E4SConv pf = p;                          // the fast form also covers a residual added before the activation (ResNet blocks)
     pf.res = nullptr;
     if (tc_epi_is_fast(pf) && !(p.res && p.res_after_act)) {
@@ -327,6 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
         if (live) tc_epilogue16(p, acc, n_base + c0, er);
       }
     }
+    }   // !split-K
     tc_fence_before();
   } else if (warp == TC_PRODUCER_WARPS) {
     // =========================== MMA issuer (whole warp walks the loop, one elected lane issues) ====
@@ -366,19 +393,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     {
       const int phases = up ? 4 : 1;
       const int64_t chunk_bytes = 2 * (int64_t)phases * B_BYTES;             // [hi: phases][lo: phases] per (n_tile, chunk)
-      const uint8_t* src = wpk + (int64_t)n_tile * num_kc * chunk_bytes + (int64_t)phase_id * B_BYTES;
+      const uint8_t* src = wpk + (int64_t)n_tile * num_kc_all * chunk_bytes + (int64_t)phase_id * B_BYTES;
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % STAGES;
         const uint32_t par = (kc / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, par ^ 1);
         const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * TC_A_BYTES;
         if (elect_one()) {
+          const int64_t koff = (int64_t)(kc_base + kc) * chunk_bytes;
           mbar_arrive_expect_tx(bar_full + 8 * s, 2 * B_BYTES);
           if (phases == 1) {
-            bulk_g2s(dst, src + kc * chunk_bytes, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous
+            bulk_g2s(dst, src + koff, 2 * B_BYTES, bar_full + 8 * s);   // B_hi | B_lo are contiguous
           } else {
-            bulk_g2s(dst, src + kc * chunk_bytes, B_BYTES, bar_full + 8 * s);
-            bulk_g2s(dst + B_BYTES, src + kc * chunk_bytes + (int64_t)phases * B_BYTES, B_BYTES, bar_full + 8 * s);
+            bulk_g2s(dst, src + koff, B_BYTES, bar_full + 8 * s);
+            bulk_g2s(dst + B_BYTES, src + koff + (int64_t)phases * B_BYTES, B_BYTES, bar_full + 8 * s);
           }
         }
         __syncwarp();
@@ -448,7 +476,7 @@ static bool tc_shape_ok(int k, int cout) {
 }
 
 template <int BN>
-static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStream_t s) {
+static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStream_t s, int ksplit = 1, float* part = nullptr) {
   static bool attr_set_dev[E4S_MAX_DEVICES] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
@@ -457,10 +485,10 @@ static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStr
     attr_set = true;
   }
   const bool up = p->mode == E4S_CONV_UP2_POLYPHASE;
-  dim3 grid((unsigned)ceil_div64(m_total, TC_BM), (unsigned)(p->cout / BN), up ? 4 : 1);
+  dim3 grid((unsigned)ceil_div64(m_total, TC_BM), (unsigned)(p->cout / BN), ksplit > 1 ? (unsigned)ksplit : (up ? 4u : 1u));
   const int gw = up ? p->win : p->wout, gh = up ? p->hin : p->hout;
   const int tile2d = (gw % 8 == 0 && gh % 16 == 0) ? 1 : 0;       // full 16x8 tiles only (tile count is the same)
-  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, tile2d);
+  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, tile2d, ksplit, part);
   return check_launch("e4s_conv_tc");
 }
 
@@ -490,6 +518,85 @@ extern "C" int e4s_pack_weights_tc_fmt(const float* w_f32, int phases, int k, in
   if (g > 148 * 32) g = 148 * 32;
   pack_weights_tc_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(w_f32, phases, k, cin, cout, cout_pad, bn, static_cast<uint8_t*>(w_packed), total, fmt, scale);
   return check_launch("pack_weights_tc");
+}
+
+namespace e4s {
+// out[pix, n] = act( (sum_z part[z][pix][n]) * corr * demod[b, r(pix), n] * ch_scale[n] + noise_w * noise[pix] + ch_shift[n] )   (fast epilogue family)
+__global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const E4SConv p, const float* __restrict__ part, const int ksplit, const int64_t m_total,
+                                                                  const float corr) {
+  const int c4 = p.cout >> 2;
+  const int64_t total = m_total * c4;
+  const float gain = p.act == E4S_ACT_LRELU ? p.act_gain : 1.f;
+  const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % c4) * 4;
+    const int64_t pix = i / c4;
+    const int ox = (int)(pix % p.wout);
+    const int64_t t = pix / p.wout;
+    const int oy = (int)(t % p.hout), b = (int)(t / p.hout);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < ksplit; ++z) {                                   // fixed order: deterministic, batch-invariant
+      const float4 v = *reinterpret_cast<const float4*>(part + ((int64_t)z * m_total + pix) * p.cout + n);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    int r = 0;
+    if (p.labels) r = p.labels[((int64_t)b * p.lab_h + nearest_src(oy, p.lab_h, p.hout)) * p.lab_w + nearest_src(ox, p.lab_w, p.wout)];
+    float4 mul = p.demod ? ldg4(p.demod + ((int64_t)b * p.regions + r) * p.cout + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.ch_scale) {
+      const float4 sc = ldg4(p.ch_scale + n);
+      mul.x *= sc.x; mul.y *= sc.y; mul.z *= sc.z; mul.w *= sc.w;
+    }
+    const float4 add = p.ch_shift ? ldg4(p.ch_shift + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float nz = p.noise ? nw * __ldg(p.noise + (int64_t)b * p.noise_sb + (int64_t)oy * p.wout + ox) : 0.f;
+    const float4 sl = make_float4(tc_epi_slope(p, n), tc_epi_slope(p, n + 1), tc_epi_slope(p, n + 2), tc_epi_slope(p, n + 3));
+    a.x = fmaf(a.x * corr, mul.x, add.x + nz); a.y = fmaf(a.y * corr, mul.y, add.y + nz);
+    a.z = fmaf(a.z * corr, mul.z, add.z + nz); a.w = fmaf(a.w * corr, mul.w, add.w + nz);
+    a.x = (a.x < 0.f ? a.x * sl.x : a.x) * gain; a.y = (a.y < 0.f ? a.y * sl.y : a.y) * gain;
+    a.z = (a.z < 0.f ? a.z * sl.z : a.z) * gain; a.w = (a.w < 0.f ? a.w * sl.w : a.w) * gain;
+    *reinterpret_cast<float4*>(p.out + pix * p.out_pitch + n) = a;
+  }
+}
+}  // namespace e4s
+
+// Split-K form of e4s_conv_tc for layers with too few output tiles to fill the machine (the generator's 4^2 - 16^2 layers: M = batch*16 ...
+// batch*256 pixels, K = 4608): ksplit CTAs per output tile each accumulate num_kc / ksplit K chunks, a second kernel adds the partial
+// accumulators in index order and applies the epilogue.  Restrictions: mode NORMAL, bf16 split, the piecewise-linear epilogue family
+// (tc_epi_is_fast), no fused ToRGB, ksplit divides the number of 64-wide K chunks.  ws: ksplit * batch*hout*wout * cout floats.
+extern "C" int64_t e4s_conv_tc_splitk_ws_bytes(const E4SConv* p, int ksplit) {
+  if (!p || ksplit < 1) return 0;
+  return (int64_t)ksplit * p->batch * p->hout * p->wout * p->cout * 4;
+}
+
+extern "C" int e4s_conv_tc_splitk(const E4SConv* p, const void* w_packed, int ksplit, void* ws, void* stream) {
+  int rc = validate_conv(p);
+  if (rc) return rc;
+  E4S_REQUIRE(w_packed && ws && ksplit >= 2 && ksplit <= 64, "conv_tc_splitk: bad args");
+  const int K = p->kh * p->kw * p->cin;
+  E4S_REQUIRE(tc_shape_ok(K, p->cout), "conv_tc_splitk: needs cin %% 8 == 0 and cout in {32,64,128,256*n} (cin=%d cout=%d)", p->cin, p->cout);
+  E4S_REQUIRE(p->mode == E4S_CONV_NORMAL && p->tc_fmt == E4S_TC_BF16 && !p->in_square && !p->rgb && tc_epi_is_fast(*p) && p->out,
+              "conv_tc_splitk: unsupported mode / operand format / epilogue option");
+  const int num_kc = (K + TC_BK - 1) / TC_BK;
+  E4S_REQUIRE(num_kc % ksplit == 0, "conv_tc_splitk: ksplit=%d must divide the %d K chunks", ksplit, num_kc);
+  E4S_REQUIRE(p->out_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (!p->smod || (reinterpret_cast<uintptr_t>(p->smod) & 15) == 0) &&
+                  (!p->demod || (reinterpret_cast<uintptr_t>(p->demod) & 15) == 0),
+              "conv_tc_splitk: pointers must be 16-byte aligned, out_pitch %% 4 == 0");
+  const int64_t m_total = (int64_t)p->batch * p->hout * p->wout;
+  cudaStream_t s = as_stream(stream);
+  float* part = static_cast<float*>(ws);
+  switch (tc_block_n(p->cout)) {
+    case 256: rc = launch_tc<256>(p, w_packed, m_total, s, ksplit, part); break;
+    case 128: rc = launch_tc<128>(p, w_packed, m_total, s, ksplit, part); break;
+    case 64: rc = launch_tc<64>(p, w_packed, m_total, s, ksplit, part); break;
+    case 32: rc = launch_tc<32>(p, w_packed, m_total, s, ksplit, part); break;
+    default: return fail(E4S_ERR_UNSUPPORTED, "conv_tc_splitk: unsupported cout %d", p->cout);
+  }
+  if (rc) return rc;
+  const float corr = tc_acc_unbias(*p, (num_kc / ksplit) * (TC_BK / 16) * 3);
+  int64_t g = ceil_div64(m_total * (p->cout / 4), 256);
+  if (g > 148 * 8) g = 148 * 8;
+  conv_splitk_epilogue_kernel<<<(unsigned)g, 256, 0, s>>>(*p, part, ksplit, m_total, corr);
+  return check_launch("e4s_conv_tc_splitk(epilogue)");
 }
 
 extern "C" int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream) {

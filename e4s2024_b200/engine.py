@@ -104,6 +104,19 @@ def wide_eligible(cin: int, cout: int, hin: int, win: int, up2: bool) -> bool:
 WIDE_OVER_REGION_JOBS = float(os.environ.get("E4S_WIDE_RATIO", "1.25"))
 
 
+def splitk_factor(hout: int, wout: int, k: int) -> int:
+    """K slices for the generator's smallest layers (e4s_conv_tc_splitk).  Chosen from the layer's geometry ONLY -- never from the batch --
+    so that a sample computed alone and inside a batch sees the same summation order (bit-exact batch invariance)."""
+    num_kc = (k + 63) // 64
+    hw = hout * wout
+    if os.environ.get("E4S_SPLITK", "1") == "0" or hw > 256 or num_kc < 16:
+        return 1
+    for ks in range(8 if hw <= 64 else 4, 1, -1):        # per-CTA fixed cost (~15 us) against 0.6-1 us per chunk: few, longer slices win
+        if num_kc % ks == 0:
+            return ks
+    return 1
+
+
 def upz_eligible(cin: int, cout: int, regional: bool = True) -> bool:
     """Mirror of e4s_conv_tc_upz's shape check: up-convolutions that can run as the conv_transpose cell GEMM + FIR pass --
     regional (masked) layers over (cell, region) rows, un-masked layers in the direct form (one row per cell, also cout 32 / 64)."""
@@ -304,8 +317,17 @@ def conv(x: View, pw: PackedConv, *, stride=1, pad=None, up2=False, in_shift=0, 
         z = torch.empty(upz.max_rows * 4 * pw.cout, device=x.t.device, dtype=torch.float32)
         L.conv_upz(p, pw.tc9, pw.fir, upz.cells, upz.rows, upz.count_dev, upz.max_rows, z)
 
+    # the generator's 4^2 - 16^2 modulated layers: a handful of output tiles, 72 K chunks each -> split-K (deterministic two-pass reduction)
+    ksplit = 1
+    if use_tc and not up2 and smod is not None and pw.tc_fmt == L.TC_BF16 and stride == 1 and in_shift == 0 and in_stats is None and rgb is None and \
+            res is None and pixw is None and not accumulate and (noise is None or noise.shape[1] == 1) and prelu is None and \
+            act in (L.ACT_NONE, L.ACT_LRELU, L.ACT_RELU) and not in_square and out is not None:
+        ksplit = splitk_factor(hout, wout, pw.k)
+
     def launch():
-        if use_upz_direct:
+        if ksplit > 1:
+            L.conv_splitk(p, pw.tc, ksplit)
+        elif use_upz_direct:
             n_cells = b * (hin + 1) * (win + 1)
             z = torch.empty(n_cells * 4 * pw.cout, device=x.t.device, dtype=torch.float32)
             L.conv_upz(p, pw.tc9, pw.fir, None, None, None, n_cells, z)

@@ -131,6 +131,13 @@ int e4s_conv_f32_batched(const E4SConv* params, int count, void* stream);
 /* tcgen05 (5th-gen tensor core) implicit GEMM with the 3-pass bf16 hi/lo split (fp32 accumulate in TMEM).
  * w points to the packed bf16 image produced by e4s_pack_weights_tc; cin % 8 == 0, cout in {32,64,128,256*n}. */
 int e4s_conv_tc(const E4SConv* p, const void* w_packed, void* stream);
+/* Split-K form of e4s_conv_tc for layers with too few output tiles to fill the machine (the generator's 4^2 - 16^2 layers: K = 4608 over
+ * batch*16 ... batch*256 output pixels): ksplit CTAs per 128-pixel tile each accumulate 1/ksplit of the 64-wide K chunks into
+ * ws[z][pixel][cout] (raw fp32 accumulators), a second kernel adds the slices in index order (deterministic) and applies the epilogue.
+ * Restrictions: mode E4S_CONV_NORMAL, bf16 split, the piecewise-linear epilogue family (no residual / float mask / accumulate / per-channel
+ * noise), no fused ToRGB, ksplit in [2, 64] dividing ceil(kh*kw*cin / 64).  ws: e4s_conv_tc_splitk_ws_bytes bytes, 16-byte aligned. */
+int64_t e4s_conv_tc_splitk_ws_bytes(const E4SConv* p, int ksplit);
+int e4s_conv_tc_splitk(const E4SConv* p, const void* w_packed, int ksplit, void* ws, void* stream);
 /* Regional (masked) 3x3 / up-conv layer through the halo kernel: `jobs` holds one int4 (b, y0, x0, region) per (16x8 tile,
  * region present in the tile), built on the device by e4s_region_tile_jobs; job_count is the device counter, job_count_host
  * its value.  Every output pixel is written by exactly one job (the one of its own region). */
