@@ -29,7 +29,8 @@ struct TcRow {
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int BN>
+// SPLITK is a template parameter: the plain instantiation sits at the register cap (168) and must not pay for the extra state.
+template <int BN, bool SPLITK = false>
 // ksplit > 1 (split-K, same-resolution / strided layers only): blockIdx.z selects a slice of num_kc / ksplit K chunks and the CTA writes its
 // RAW partial accumulator to part[z][output pixel][cout]; e4s_conv_tc_splitk's second kernel adds the slices in index order and applies the
 // epilogue.  For the generator's 4^2-16^2 layers: a handful of CTAs walking 72 chunks each otherwise (0.17-0.2 ms of pure latency).
@@ -55,12 +56,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
   float* sv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + TC_BM * 16 + 256);   // [mul | add | slope] x BN: this CTA's channels
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int phase_id = ksplit > 1 ? 0 : (int)blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
+  const int phase_id = SPLITK ? 0 : (int)blockIdx.z, py = phase_id >> 1, px = phase_id & 1;
   const int n_tile = blockIdx.y;
   const int K = p.kh * p.kw * p.cin;
   const int num_kc_all = (K + TC_BK - 1) / TC_BK;   // K is zero-padded to a multiple of 64 in the packed weights
-  const int num_kc = num_kc_all / ksplit;           // chunks of this CTA's K slice (the host makes ksplit divide the chunk count)
-  const int kc_base = ksplit > 1 ? (int)blockIdx.z * num_kc : 0;
+  const int num_kc = SPLITK ? num_kc_all / ksplit : num_kc_all;   // chunks of this CTA's K slice (the host makes ksplit divide the chunk count)
+  const int kc_base = SPLITK ? (int)blockIdx.z * num_kc : 0;
   const bool up = p.mode == E4S_CONV_UP2_POLYPHASE;
 
   // ---- one-time setup ---------------------------------------------------------------------------
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const E4SConv p,
     er.nw = p.noise ? __ldg(p.noise_w) : 0.f;
     er.nrow = (p.noise && live) ? p.noise + (int64_t)rw.b * p.noise_sb + (int64_t)rw.oy * p.wout + rw.ox : nullptr;
     er.nz = (er.nrow && p.noise_sc == 0) ? er.nw * __ldg(er.nrow) : 0.f;
-    if (ksplit > 1) {
+    if (SPLITK) {
       // split-K: the raw accumulator of this K slice -> part[z][pixel][cout] (the reduction kernel applies un-bias, demodulation, epilogue)
       float* prow = part + ((int64_t)blockIdx.z * m_total + pix) * p.cout + n_base;
 #pragma unroll 1
@@ -480,7 +481,8 @@ static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStr
   static bool attr_set_dev[E4S_MAX_DEVICES] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
     if (e != cudaSuccess) return fail(E4S_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -488,7 +490,8 @@ static int launch_tc(const E4SConv* p, const void* wpk, int64_t m_total, cudaStr
   dim3 grid((unsigned)ceil_div64(m_total, TC_BM), (unsigned)(p->cout / BN), ksplit > 1 ? (unsigned)ksplit : (up ? 4u : 1u));
   const int gw = up ? p->win : p->wout, gh = up ? p->hin : p->hout;
   const int tile2d = (gw % 8 == 0 && gh % 16 == 0) ? 1 : 0;       // full 16x8 tiles only (tile count is the same)
-  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, tile2d, ksplit, part);
+  if (ksplit > 1) conv_tc_kernel<BN, true><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, tile2d, ksplit, part);
+  else conv_tc_kernel<BN, false><<<grid, TC_THREADS, tc_smem_bytes(BN), s>>>(*p, static_cast<const uint8_t*>(wpk), m_total, tile2d, 1, nullptr);
   return check_launch("e4s_conv_tc");
 }
 
