@@ -10,7 +10,7 @@ constexpr int STATS_MAX_SPLIT = 32;
 
 __host__ __device__ inline int stats_split(int batch, int hw, int c) {
   int groups = batch * ((c + 31) / 32);
-  int s = (592 + groups - 1) / groups;
+  int s = (592 + groups - 1) / groups;           // ~4 blocks per SM (12 measured slower: 13.2 vs 12.8 ms for the encoder stage)
   int cap = hw / 64;
   if (s > cap) s = cap;
   if (s > STATS_MAX_SPLIT) s = STATS_MAX_SPLIT;
