@@ -263,8 +263,10 @@ def stage_breakdown(hot, img_u8_d, steps=5):
         fn()
     torch.cuda.synchronize()
     prof, E.PROFILE, E.PROFILE_STAGE = E.PROFILE, None, None
-    ctx = E.RegionCtx(mask, net.G._region_job_keys(), lazy=False)          # how the parser's masks tile: region jobs per 16x8 tile
+    # how the parser's masks tile: region jobs per 16x8 tile (masked same-resolution layers) and (cell, region) rows per cell (masked up-convolutions)
+    ctx = E.RegionCtx(mask, net.G._region_job_keys(), lazy=False, upz_keys=net.G._upz_keys())
     ms["mask_region_jobs_per_tile"] = {f"{h}x{w}{'_up' if up else ''}": round(rj.count / max(rj.tiles, 1), 3) for (h, w, up), rj in ctx.region_jobs.items()}
+    ms["mask_upconv_rows_per_cell"] = {f"{h}x{w}->{2 * h}x{2 * w}": round(uz.count / max(uz.cells_total, 1), 3) for (h, w), uz in ctx.upz.items()}
     return ms, prof
 
 
@@ -313,9 +315,10 @@ def generator_only(dev, steps):
     for kind in ("blocky", "face", "noise"):
         mask = synth.onehot(synth.make_labels(kind, BATCH, K, 512, seed=1), K).to(dev)
         ms, _ = time_steps(lambda: G([latent], None, mask, input_is_latent=True, randomize_noise=False), steps, warmup=3)
-        ctx = E.RegionCtx(mask, G._region_job_keys(), lazy=False)        # synchronous context: job counts for the report
+        ctx = E.RegionCtx(mask, G._region_job_keys(), lazy=False, upz_keys=G._upz_keys())        # synchronous context: counts for the report
         jobs = {f"{h}x{w}{'_up' if up else ''}": round(rj.count / max(rj.tiles, 1), 3) for (h, w, up), rj in ctx.region_jobs.items()}
-        out["masks"][kind] = {"value": BATCH / ms * 1e3, "unit": "faces/s", "ms_per_step": ms, "region_jobs_per_tile": jobs,
+        rows = {f"{h}x{w}->{2 * h}x{2 * w}": round(uz.count / max(uz.cells_total, 1), 3) for (h, w), uz in ctx.upz.items()}
+        out["masks"][kind] = {"value": BATCH / ms * 1e3, "unit": "faces/s", "ms_per_step": ms, "region_jobs_per_tile": jobs, "upconv_rows_per_cell": rows,
                               "alg_tflops": BATCH / ms * ALG_GFLOP["generator"]}
     out["mask_kinds"] = {"blocky": "random class per 32x32 cell of the 512^2 label map (tile-aligned at every resolution >= 64^2)",
                          "face": "procedural face (ellipses, curved boundaries; regions per 16x8 tile 1.4 / 1.8 / 2.7 / 4.9 at 256^2 / 128^2 / 64^2 / 32^2, "
