@@ -212,7 +212,12 @@ __global__ void labels_to_onehot_kernel(const uint8_t* __restrict__ labels, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int TORGB_TILE_MAX = 256;
 
-template <int LP, int TORGB_TILE>
+// TAB (large images, cin <= 256, regions <= 12, tiles that lie inside one sample): the CTA first builds the MODULATED weights
+// wm[region][3][cin] = wrgb * smod[b, region] of its sample in shared memory, so that a pixel step loads only its features from global
+// memory (one float4 per lane and channel step instead of five: features, style row and three weight rows) -- the kernel was
+// load-issue bound at 1.5 TB/s on the 128^2 / 256^2 layers.
+constexpr int TORGB_TAB_R = 12, TORGB_TAB_C = 256;
+template <int LP, int TORGB_TILE, bool TAB = false>
 __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, int64_t x_pitch, int64_t npix, int h, int w,
                                                     int cin, const float* __restrict__ smod, const float* __restrict__ wrgb,
                                                     const uint8_t* __restrict__ labels, int regions, int lab_h, int lab_w,
@@ -221,10 +226,21 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ fir, float* __restrict__ rgb, int accumulate) {
   constexpr int PPW = 32 / LP;  // pixels per warp step
   __shared__ float srgb[3][TORGB_TILE];
+  __shared__ __align__(16) float wm[TAB ? TORGB_TAB_R * 3 * TORGB_TAB_C : 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LP, ll = lane % LP;
   const int hw = h * w;
   const int64_t tile0 = (int64_t)blockIdx.x * TORGB_TILE;
+  if (TAB) {
+    const int b0 = (int)(tile0 / hw);                  // the host guarantees hw % TORGB_TILE == 0: one sample per tile
+    const int n = regions * 3 * cin;
+    for (int idx = threadIdx.x; idx < n; idx += 256) {
+      const int r = idx / (3 * cin), rem = idx - r * 3 * cin;
+      const int c = rem / cin, ci = rem - c * cin;
+      wm[idx] = __ldg(wrgb + c * cin + ci) * __ldg(smod + ((int64_t)b0 * regions + r) * cin + ci);
+    }
+    __syncthreads();
+  }
   // ---- phase A: dot products ---------------------------------------------------------------------
   // TU pixels per warp step with independent accumulators: every step is a chain of dependent global loads (label ->
   // style row -> features), and one pixel per step made the kernel pure latency (90 us per launch whatever the grid size).
@@ -234,6 +250,7 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
     float a0[TU], a1[TU], a2[TU];
     const float* xr[TU];
     const float* sr[TU];
+    int rg[TU];
     bool ok[TU];
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
@@ -243,6 +260,7 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
       ok[u] = t < TORGB_TILE && pix < npix;
       xr[u] = x;
       sr[u] = smod;
+      rg[u] = 0;
       if (ok[u]) {
         const int b = (int)(pix / hw);
         int r = 0;
@@ -253,8 +271,36 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
         }
         xr[u] = x + pix * x_pitch;
         sr[u] = smod + ((int64_t)b * regions + r) * cin;
+        rg[u] = r;
       }
     }
+    if (TAB) {
+      for (int ci0 = ll * 4; ci0 < cin; ci0 += LP * 4 * NCI) {
+        float4 v[TU][NCI];
+#pragma unroll
+        for (int k = 0; k < NCI; ++k) {
+          const int ci = ci0 + k * LP * 4;
+#pragma unroll
+          for (int u = 0; u < TU; ++u)
+            v[u][k] = (ci < cin && ok[u]) ? __ldg(reinterpret_cast<const float4*>(xr[u] + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < NCI; ++k) {
+          const int ci = ci0 + k * LP * 4;
+          if (ci >= cin) continue;
+#pragma unroll
+          for (int u = 0; u < TU; ++u) {
+            const float* wr = wm + rg[u] * 3 * cin + ci;
+            const float4 q = v[u][k];
+            const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + cin),
+                         w2 = *reinterpret_cast<const float4*>(wr + 2 * cin);
+            a0[u] += q.x * w0.x + q.y * w0.y + q.z * w0.z + q.w * w0.w;
+            a1[u] += q.x * w1.x + q.y * w1.y + q.z * w1.z + q.w * w1.w;
+            a2[u] += q.x * w2.x + q.y * w2.y + q.z * w2.z + q.w * w2.w;
+          }
+        }
+      }
+    } else
     for (int ci0 = ll * 4; ci0 < cin; ci0 += LP * 4 * NCI) {
       float4 w0[NCI], w1[NCI], w2[NCI], v[TU][NCI], sm[TU][NCI];
 #pragma unroll
@@ -275,11 +321,15 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
       for (int k = 0; k < NCI; ++k)          // same order of additions per pixel as one channel step at a time
 #pragma unroll
         for (int u = 0; u < TU; ++u) {
-          float4 q = v[u][k];
-          q.x *= sm[u][k].x; q.y *= sm[u][k].y; q.z *= sm[u][k].z; q.w *= sm[u][k].w;
-          a0[u] += q.x * w0[k].x + q.y * w0[k].y + q.z * w0[k].z + q.w * w0[k].w;
-          a1[u] += q.x * w1[k].x + q.y * w1[k].y + q.z * w1[k].z + q.w * w1[k].w;
-          a2[u] += q.x * w2[k].x + q.y * w2[k].y + q.z * w2[k].z + q.w * w2[k].w;
+          // x * (w * s), the association of the TAB path (whose table holds w * s): which path a launch takes depends on the batch
+          // size, and a sample must come out bit-identical alone and inside a batch
+          const float4 q = v[u][k], s4 = sm[u][k];
+          const float4 m0 = make_float4(w0[k].x * s4.x, w0[k].y * s4.y, w0[k].z * s4.z, w0[k].w * s4.w);
+          const float4 m1 = make_float4(w1[k].x * s4.x, w1[k].y * s4.y, w1[k].z * s4.z, w1[k].w * s4.w);
+          const float4 m2 = make_float4(w2[k].x * s4.x, w2[k].y * s4.y, w2[k].z * s4.z, w2[k].w * s4.w);
+          a0[u] += q.x * m0.x + q.y * m0.y + q.z * m0.z + q.w * m0.w;
+          a1[u] += q.x * m1.x + q.y * m1.y + q.z * m1.z + q.w * m1.w;
+          a2[u] += q.x * m2.x + q.y * m2.y + q.z * m2.z + q.w * m2.w;
         }
     }
 #pragma unroll
@@ -448,11 +498,16 @@ extern "C" int e4s_torgb_f32(const float* x, int64_t x_pitch, int batch, int h, 
   // the other (the kernel is a chain of dependent L2 round trips per pixel step: 75-90 us per launch whatever the size before)
   const bool small = npix <= 32 * 148 * 16;
   const unsigned tiles = (unsigned)ceil_div64(npix, small ? 32 : 256);
+  // modulated-weight table in shared memory (see torgb_kernel): large images whose 256-pixel tiles never straddle two samples
+  const bool tab = !small && cin >= 128 && cin <= TORGB_TAB_C && regions <= TORGB_TAB_R && ((int64_t)h * w) % 256 == 0 && cin % 4 == 0;
 #define E4S_TORGB_LAUNCH(LPV)                                                                                                        \
   do {                                                                                                                             \
     if (small)                                                                                                                     \
       torgb_kernel<LPV, 32><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w, pixw, pixw_sb, \
                                                   bias, skip, fir, rgb, accumulate);                                                \
+    else if (tab)                                                                                                                  \
+      torgb_kernel<LPV, 256, true><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w, pixw,  \
+                                                         pixw_sb, bias, skip, fir, rgb, accumulate);                                  \
     else                                                                                                                           \
       torgb_kernel<LPV, 256><<<tiles, 256, 0, s>>>(x, x_pitch, npix, h, w, cin, smod, wrgb, labels, regions, lab_h, lab_w, pixw, pixw_sb, \
                                                    bias, skip, fir, rgb, accumulate);                                               \
